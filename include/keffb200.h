@@ -1,0 +1,135 @@
+/* keffb200.h -- C ABI of the B200-native Keff-CFD hot path.
+ *
+ * The reference (adama-wzr/Keff-CFD) has no plugin/FFI layer: the seam is the solver call inside
+ * each program's main().  Every entry point below names the reference call site it replaces.
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer; the library owns
+ * all device memory, streams and communicator state; no exit(), no stdin, no stdout; every function
+ * returns 0 on success or a negative KEFFB200_E* code, with text from keffb200_last_error().
+ * One context per process (one process per GPU); calls are not re-entrant.
+ *
+ * Structure semantics are fixed at this boundary: `solid` is one byte per cell, 1 = solid (ks),
+ * anything else = fluid (kf); layout [z][y][x], x fastest -- the reference's
+ * index = z*ny*nx + y*nx + x (Keff3D/keff3D.h:691).  The host maps its inputs onto it:
+ * 2D JPG pixel >= 150 -> solid (Keff2D/keff2D.cpp:113-119), 3D voxel listed in the CSV -> solid
+ * (Keff3D/keff3D.h:269-277, keff3D.cpp:113-117); MeshAmp replication is done by the host.
+ * The physical domain is the unit square/cube, T = tl on the x = 0 face and tr on the x = 1 face,
+ * all other faces adiabatic (Keff2D/keff2D.h:482-582, Keff3D/keff3D.h:666-763).
+ */
+#ifndef KEFFB200_H
+#define KEFFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KEFFB200_OK 0
+#define KEFFB200_ENOGPU (-1)   /* no CUDA device / not sm_100 */
+#define KEFFB200_EINVAL (-2)   /* bad argument */
+#define KEFFB200_ECUDA (-3)    /* CUDA runtime error (text in last_error) */
+#define KEFFB200_ENOMEM (-4)
+#define KEFFB200_ENCCL (-5)    /* NCCL missing or failed */
+#define KEFFB200_ESTATE (-6)   /* init not called, or slab calls without dist_init */
+
+/* Solver knobs.  The first six are the reference's input.txt keys that reach the path
+ * (ks kf TL TR Convergence MaxIter: Keff2D/keff2D.h:142-205, Keff3D/keff3D.h:145-220).  The rest
+ * have no reference counterpart; 0 selects the default. */
+typedef struct keffb200_params {
+  double ks, kf;          /* TCsolid, TCfluid */
+  double tl, tr;          /* TempLeft, TempRight */
+  double convergence;     /* ConvergeCriteria: max relative change of Keff between two checks */
+  long max_iter;          /* MAX_ITER: cap on solver iterations */
+  double rel_residual;    /* stop when ||b - A T||2 / ||b||2 <= this (default 1e-8) */
+  double flux_balance;    /* ... and |QL - QR| / |Keff| <= this (default 1e-6) */
+  int check_every;        /* iterations between host-visible convergence checks (default 32) */
+  int flags;              /* KEFFB200_F_* */
+} keffb200_params;
+
+#define KEFFB200_F_NO_TMA 1      /* use the plain global-load stencil kernel (debug / odd nx) */
+#define KEFFB200_F_ZERO_INIT 2   /* start from T = tl everywhere (the reference's actual T0,
+                                    Keff2D/keff2D.h:584-611) instead of the linear ramp */
+
+/* Per-solve record: the numbers the reference puts in its CSV row (keff, QL, QR, Iter:
+ * Keff2D/keff2D.h:245-246) plus what its GPU variant keeps in simulationInfo
+ * (Keff2DGPU/keff2D.cuh:41-55: keff, conv, gpuTime). */
+typedef struct keffb200_result {
+  double keff;            /* (QL + QR) / 2 / (tr - tl) */
+  double q_left, q_right; /* sum of face fluxes through x = 0 and x = 1 (Q1, Q2) */
+  double rel_residual;    /* TRUE ||b - A T||2 / ||b||2 of the returned field */
+  double energy_residual; /* sum_cells |net flux imbalance| = reference Residual() (keff2D.h:384) */
+  long iters;             /* solver iterations taken */
+  int status;             /* 0 converged, 1 stopped at max_iter */
+  float gpu_ms;           /* device time of the solve, CUDA events */
+} keffb200_result;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+/* Bind the process to CUDA device `device` (replaces initializeGPU's cudaSetDevice(0),
+ * Keff2DGPU/keff2D.cuh:606-683; memory is allocated lazily by the solves and cached). */
+int keffb200_init(int device);
+void keffb200_shutdown(void); /* replaces unInitializeGPU, Keff2DGPU/keff2D.cuh:685-723 */
+const char* keffb200_last_error(void);
+const char* keffb200_version(void);
+void keffb200_default_params(keffb200_params* p); /* shipped input.txt values: ks 10 kf 1 TL 0 TR 1
+                                                     Convergence 1e-5 MaxIter 500000 */
+/* Count of this library's kernel launches since init (bench.py's gpu_launches). */
+long keffb200_launch_count(void);
+
+/* ---- whole-path solves, HOST buffers (the reference-facing calls) ----------------------------- */
+/* One 2D image.  Replaces DiscretizeMatrixCD2D + SolInitLinear + ParallelGS + the flux loop at
+ * Keff2D/keff2D.cpp:131-170 (and DiscretizeMatrix2D + JacobiGPU, Keff2DGPU/keff2D.cuh:969-974).
+ * T_init (nullable, ny*nx) warm start; T_out (nullable, ny*nx); qL,qR (nullable, ny) per-row fluxes. */
+int keffb200_solve2d(const uint8_t* solid, int nx, int ny, const keffb200_params* p, const double* T_init,
+                     double* T_out, double* qL, double* qR, keffb200_result* out);
+
+/* A batch of independent equally-sized 2D images (n_img*ny*nx bytes).  Replaces the batch loops
+ * Keff2D/keff2D.cpp:341-471 (OpenMP over images, SerialGS each) and BatchSim
+ * Keff2DGPU/keff2D.cuh:1007-1168.  out[n_img].  T_out nullable (n_img*ny*nx). */
+int keffb200_solve2d_batch(const uint8_t* solid, int n_img, int nx, int ny, const keffb200_params* p,
+                           double* T_out, keffb200_result* out);
+
+/* One 3D volume on this process's GPU.  Replaces DiscretizeMatrixCD3D + SolInitLinear +
+ * ParallelGS3D + the flux loop at Keff3D/keff3D.cpp:134-163.  qL,qR nullable, nz*ny each. */
+int keffb200_solve3d(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p,
+                     const double* T_init, double* T_out, double* qL, double* qR, keffb200_result* out);
+
+/* ---- the same solves on DEVICE buffers (inputs already resident in HBM) ----------------------- */
+int keffb200_solve3d_dev(const uint8_t* d_solid, int nx, int ny, int nz, const keffb200_params* p,
+                         const double* d_T_init, double* d_T_out, keffb200_result* out);
+int keffb200_solve2d_batch_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params* p,
+                               double* d_T_out, keffb200_result* out /* host */);
+
+/* ---- z-slab decomposition across processes (one process per GPU) ------------------------------ */
+/* Size of the opaque communicator id that rank 0 creates and the host broadcasts to all ranks. */
+#define KEFFB200_COMM_ID_BYTES 128
+int keffb200_comm_id(void* id128);                       /* rank 0: ncclGetUniqueId */
+int keffb200_dist_init(int rank, int world, const void* id128); /* all ranks: ncclCommInitRank */
+void keffb200_dist_shutdown(void);
+/* Solve a global nx*ny*nz_global volume whose planes [z0, z0+nz_local) live on this rank.
+ * d_solid_halo: (nz_local+2) planes, plane 0 / plane nz_local+1 = the neighbouring ranks' boundary
+ * planes (ignored at the global ends).  d_T_out: nz_local planes (nullable).  Collective: every rank
+ * of the communicator must call it; every rank receives the same result. */
+int keffb200_solve3d_slab_dev(const uint8_t* d_solid_halo, int nx, int ny, int nz_local, int z0,
+                              int nz_global, const keffb200_params* p, double* d_T_out,
+                              keffb200_result* out);
+
+/* ---- pieces of the path, exposed for parity tests and roofline measurement -------------------- */
+/* y = A x, the matrix-free form of the system DiscretizeMatrixCD2D/3D assembles
+ * (Keff2D/keff2D.h:482-582, Keff3D/keff3D.h:666-763); b (nullable) receives the right-hand side.
+ * Host buffers, nz = 1 for 2D. */
+int keffb200_apply(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* x,
+                   double* y, double* b);
+/* Boundary-flux integration alone (Keff2D/keff2D.cpp:151-170, Keff3D/keff3D.cpp:145-163) and the
+ * energy-imbalance Residual() (Keff2D/keff2D.h:384-424) of a given host field T. */
+int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T,
+                  double* qL, double* qR, keffb200_result* out);
+/* Timing hook: `reps` applications of the stencil kernel on device-resident data
+ * (one cell-update per cell per application, 16 B/cell of compulsory traffic).  Returns the average
+ * milliseconds per application, measured with CUDA events on the launching stream. */
+int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, const keffb200_params* p,
+                             int reps, float* ms_per_apply);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEFFB200_H */

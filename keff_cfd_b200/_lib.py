@@ -1,0 +1,102 @@
+"""ctypes binding of libkeffb200.so (the C ABI declared in include/keffb200.h).
+
+There is no CPU path: if the CUDA library is missing, or no B200 is visible when a solve is
+requested, the call raises -- it never falls back to anything else.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libkeffb200.so")
+
+
+class Params(C.Structure):
+    """keffb200_params (include/keffb200.h)."""
+    _fields_ = [("ks", C.c_double), ("kf", C.c_double), ("tl", C.c_double), ("tr", C.c_double),
+                ("convergence", C.c_double), ("max_iter", C.c_long), ("rel_residual", C.c_double),
+                ("flux_balance", C.c_double), ("check_every", C.c_int), ("flags", C.c_int)]
+
+
+class Result(C.Structure):
+    """keffb200_result (include/keffb200.h)."""
+    _fields_ = [("keff", C.c_double), ("q_left", C.c_double), ("q_right", C.c_double),
+                ("rel_residual", C.c_double), ("energy_residual", C.c_double), ("iters", C.c_long),
+                ("status", C.c_int), ("gpu_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+F_NO_TMA = 1
+F_ZERO_INIT = 2
+COMM_ID_BYTES = 128
+
+# every symbol include/keffb200.h declares (tests check the built library exports each of them)
+EXPORTS = [
+    "keffb200_init", "keffb200_shutdown", "keffb200_last_error", "keffb200_version",
+    "keffb200_default_params", "keffb200_launch_count", "keffb200_solve2d", "keffb200_solve2d_batch",
+    "keffb200_solve3d", "keffb200_solve3d_dev", "keffb200_solve2d_batch_dev", "keffb200_comm_id",
+    "keffb200_dist_init", "keffb200_dist_shutdown", "keffb200_solve3d_slab_dev", "keffb200_apply",
+    "keffb200_flux", "keffb200_bench_apply_dev",
+]
+
+_lib = None
+
+
+class KeffB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libkeffb200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KeffB200Error(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C keff_cfd_b200/csrc). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, dp, u8p = C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses: host or device
+        PP, RP = C.POINTER(Params), C.POINTER(Result)
+        L.keffb200_last_error.restype = C.c_char_p
+        L.keffb200_version.restype = C.c_char_p
+        L.keffb200_launch_count.restype = C.c_long
+        L.keffb200_init.argtypes = [C.c_int]
+        L.keffb200_default_params.argtypes = [PP]
+        L.keffb200_solve2d.argtypes = [u8p, C.c_int, C.c_int, PP, dp, dp, dp, dp, RP]
+        L.keffb200_solve2d_batch.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, RP]
+        L.keffb200_solve3d.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, dp, dp, RP]
+        L.keffb200_solve3d_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, RP]
+        L.keffb200_solve2d_batch_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, RP]
+        L.keffb200_comm_id.argtypes = [vp]
+        L.keffb200_dist_init.argtypes = [C.c_int, C.c_int, vp]
+        L.keffb200_solve3d_slab_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, PP, dp, RP]
+        L.keffb200_apply.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, dp]
+        L.keffb200_flux.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, dp, RP]
+        L.keffb200_bench_apply_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, C.c_int,
+                                               C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise KeffB200Error(f"keffb200 error {rc}: {lib().keffb200_last_error().decode()}")
+
+
+_inited = None
+
+
+def init(device=0):
+    """Bind this process to one GPU (one process per GPU)."""
+    global _inited
+    if _inited != device:
+        check(lib().keffb200_init(int(device)))
+        _inited = device
+
+
+def shutdown():
+    global _inited
+    if _lib is not None:
+        _lib.keffb200_shutdown()
+    _inited = None

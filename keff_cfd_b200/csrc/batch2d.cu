@@ -1,0 +1,262 @@
+// batch2d.cu -- batches of independent 2D images: one persistent CTA solves one image at a time.
+//
+// Replaces the reference batch loops (Keff2D/keff2D.cpp:341-471: OpenMP over images, each image
+// assembled by DiscretizeMatrixCD2D and relaxed by SerialGS; Keff2DGPU/keff2D.cuh:1007-1168:
+// BatchSim, a serial loop with cudaMalloc..cudaDeviceReset per image).  Here the whole solve of an
+// image -- code bytes, initial field, diagonally preconditioned CG, convergence control, boundary
+// flux, true residual -- runs inside one CTA with block-level reductions and no host round trip;
+// CTAs pull images from an atomic counter, so the grid stays full whatever the per-image iteration
+// counts are, and per-image results do not depend on the schedule.
+#include "context.cuh"
+#include "common.cuh"
+
+namespace kb {
+
+Coef make_coef(int nx, int ny, int nzg, const keffb200_params& P);
+
+struct BatchOut {
+  double ql, qr, rr, bb, r1;
+  long long it;
+  int status, pad;
+};
+
+template <int N>
+__device__ __forceinline__ void block_allsum(double (&v)[N], double* red, double* bc) {
+  block_sum<N>(v, red);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int j = 0; j < N; j++) bc[j] = v[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; j++) v[j] = bc[j];
+  __syncthreads();
+}
+
+// v1: CG vectors live in a per-CTA slice of global memory that stays L2-resident
+// (148 CTAs x 4 vectors x 128 KiB = 74 MiB < 126 MB L2 for 128x128 images).
+__global__ void __launch_bounds__(1024, 1)
+    k_batch2d_pcg(const uint8_t* __restrict__ masks, int n_img, int nx, int ny, const Coef C, double thr2_in,
+                  double flux_tol, long long max_iter, int const_init, double* __restrict__ ws,
+                  uint8_t* __restrict__ codes, double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter) {
+  __shared__ double red[32 * 3];
+  __shared__ double bc[4];
+  __shared__ int s_img;
+  const int n = nx * ny;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* x = ws + (size_t)blockIdx.x * 4 * n;
+  double* r = x + n;
+  double* p = r + n;
+  double* q = p + n;
+  uint8_t* code = codes + (size_t)blockIdx.x * n;
+
+  while (true) {
+    if (threadIdx.x == 0) s_img = atomicAdd(counter, 1);
+    __syncthreads();
+    const int img = s_img;
+    __syncthreads();
+    if (img >= n_img) break;
+    const uint8_t* m = masks + (size_t)img * n;
+
+    // structure -> code bytes, initial field
+    for (int row = wrp; row < ny; row += nw)
+      for (int xx = lane; xx < nx; xx += 32) {
+        const int i = row * nx + xx;
+        const unsigned me = m[i] == 1;
+        unsigned c = me;
+        if (xx > 0 && (unsigned)(m[i - 1] == 1) != me) c |= C_W;
+        if (xx < nx - 1 && (unsigned)(m[i + 1] == 1) != me) c |= C_E;
+        if (row < ny - 1 && (unsigned)(m[i + nx] == 1) != me) c |= C_S;
+        if (row > 0 && (unsigned)(m[i - nx] == 1) != me) c |= C_N;
+        code[i] = (uint8_t)c;
+        x[i] = const_init ? C.tl : C.tl + (C.tr - C.tl) * ((xx + 0.5) / nx);
+      }
+    __syncthreads();
+
+    // r = b - A x, p = z = r / a_P
+    double a3[3] = {0, 0, 0};
+    for (int row = wrp; row < ny; row += nw) {
+      const bool y0 = row == 0, y1 = row == ny - 1;
+      for (int xx = lane; xx < nx; xx += 32) {
+        const int i = row * nx + xx;
+        const bool x0 = xx == 0, x1 = xx == nx - 1;
+        const unsigned c = code[i];
+        const Faces F = faces_of(C, c, x0, x1, y0, y1, true, true);
+        double qv = F.diag * x[i];
+        if (!x0) qv -= F.w * x[i - 1];
+        if (!x1) qv -= F.e * x[i + 1];
+        if (!y0) qv -= F.n * x[i - nx];
+        if (!y1) qv -= F.s * x[i + nx];
+        const double b = rhs_of(C, c, x0, x1), rv = b - qv, z = rv / F.diag;
+        r[i] = rv;
+        p[i] = z;
+        a3[0] += rv * z;
+        a3[1] += rv * rv;
+        a3[2] += b * b;
+      }
+    }
+    block_allsum<3>(a3, red, bc);
+    double rz = a3[0], rr = a3[1];
+    const double bb = a3[2];
+    double thr2 = thr2_in;
+    long long it = 0;
+    int status = 1;
+    double ql = 0, qr = 0;
+
+    while (true) {
+      bool conv = !(rr > thr2 * bb);
+      if (conv || it >= max_iter) {
+        // boundary flux (Keff2D/keff2D.cpp:151-170); also the flux-balance part of the stop test
+        double f2[2] = {0, 0};
+        for (int row = threadIdx.x; row < ny; row += blockDim.x) {
+          const int l = row * nx, e = l + nx - 1;
+          f2[0] += ((code[l] & C_PH) ? C.wall[1] : C.wall[0]) * (x[l] - C.tl);
+          f2[1] += ((code[e] & C_PH) ? C.wall[1] : C.wall[0]) * (C.tr - x[e]);
+        }
+        block_allsum<2>(f2, red, bc);
+        ql = f2[0];
+        qr = f2[1];
+        const double keff = (ql + qr) / 2 / (C.tr - C.tl);
+        if (conv && (fabs(ql - qr) <= flux_tol * fabs(keff) || thr2 < 1e-28)) {
+          status = 0;
+          break;
+        }
+        if (it >= max_iter) break;
+        thr2 *= 1e-2;  // residual target met but wall fluxes still disagree: keep iterating
+        continue;
+      }
+      // q = A p, p.q
+      double a1[1] = {0};
+      for (int row = wrp; row < ny; row += nw) {
+        const bool y0 = row == 0, y1 = row == ny - 1;
+        for (int xx = lane; xx < nx; xx += 32) {
+          const int i = row * nx + xx;
+          const bool x0 = xx == 0, x1 = xx == nx - 1;
+          const Faces F = faces_of(C, code[i], x0, x1, y0, y1, true, true);
+          const double pc = p[i];
+          double qv = F.diag * pc;
+          if (!x0) qv -= F.w * p[i - 1];
+          if (!x1) qv -= F.e * p[i + 1];
+          if (!y0) qv -= F.n * p[i - nx];
+          if (!y1) qv -= F.s * p[i + nx];
+          q[i] = qv;
+          a1[0] += pc * qv;
+        }
+      }
+      block_allsum<1>(a1, red, bc);
+      const double alpha = rz / a1[0];
+      // x += alpha p, r -= alpha q, r.z, r.r
+      double a2[2] = {0, 0};
+      for (int row = wrp; row < ny; row += nw) {
+        const bool y0 = row == 0, y1 = row == ny - 1;
+        for (int xx = lane; xx < nx; xx += 32) {
+          const int i = row * nx + xx;
+          const double d = diag_of(C, code[i], xx == 0, xx == nx - 1, y0, y1, true, true);
+          x[i] += alpha * p[i];
+          const double rv = r[i] - alpha * q[i];
+          r[i] = rv;
+          a2[0] += rv * (rv / d);
+          a2[1] += rv * rv;
+        }
+      }
+      block_allsum<2>(a2, red, bc);
+      const double beta = a2[0] / rz;
+      rz = a2[0];
+      rr = a2[1];
+      it++;
+      // p = z + beta p
+      for (int row = wrp; row < ny; row += nw) {
+        const bool y0 = row == 0, y1 = row == ny - 1;
+        for (int xx = lane; xx < nx; xx += 32) {
+          const int i = row * nx + xx;
+          const double d = diag_of(C, code[i], xx == 0, xx == nx - 1, y0, y1, true, true);
+          p[i] = r[i] / d + beta * p[i];
+        }
+      }
+      __syncthreads();
+    }
+
+    // true residual of the returned field + optional temperature map
+    double t2[2] = {0, 0};
+    for (int row = wrp; row < ny; row += nw) {
+      const bool y0 = row == 0, y1 = row == ny - 1;
+      for (int xx = lane; xx < nx; xx += 32) {
+        const int i = row * nx + xx;
+        const bool x0 = xx == 0, x1 = xx == nx - 1;
+        const unsigned c = code[i];
+        const Faces F = faces_of(C, c, x0, x1, y0, y1, true, true);
+        double qv = F.diag * x[i];
+        if (!x0) qv -= F.w * x[i - 1];
+        if (!x1) qv -= F.e * x[i + 1];
+        if (!y0) qv -= F.n * x[i - nx];
+        if (!y1) qv -= F.s * x[i + nx];
+        const double rv = rhs_of(C, c, x0, x1) - qv;
+        t2[0] += rv * rv;
+        t2[1] += fabs(rv);
+        if (T_out) T_out[(size_t)img * n + i] = x[i];
+      }
+    }
+    block_allsum<2>(t2, red, bc);
+    if (threadIdx.x == 0) {
+      BatchOut o;
+      o.ql = ql;
+      o.qr = qr;
+      o.rr = t2[0];
+      o.bb = bb;
+      o.r1 = t2[1];
+      o.it = it;
+      o.status = status;
+      o.pad = 0;
+      res[img] = o;
+    }
+  }
+}
+
+int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params& P, double* d_T_out,
+                      keffb200_result* out) {
+  Ctx& c = ctx();
+  if (nx < 2 || ny < 2) return fail(KEFFB200_EINVAL, "image %dx%d too small", nx, ny);
+  if (P.tr == P.tl) return fail(KEFFB200_EINVAL, "TR == TL: Keff undefined");
+  const size_t n = (size_t)nx * ny;
+  const int grid = std::min(n_img, c.sms);
+  const size_t need = (size_t)grid * (4 * n * 8 + n) + (size_t)n_img * sizeof(BatchOut) + 256;
+  if (need > c.cap_batch) {
+    if (c.batch_ws) cudaFree(c.batch_ws);
+    c.batch_ws = nullptr;
+    c.cap_batch = 0;
+    KB_CUDA(cudaMalloc(&c.batch_ws, need));
+    c.cap_batch = need;
+  }
+  char* base = (char*)c.batch_ws;
+  double* ws = (double*)base;
+  BatchOut* res = (BatchOut*)(base + (size_t)grid * 4 * n * 8);
+  int* counter = (int*)(res + n_img);
+  uint8_t* codes = (uint8_t*)(counter + 16);
+  const Coef C = make_coef(nx, ny, 1, P);
+  KB_CUDA(cudaEventRecord(c.ev0, c.st));
+  KB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c.st));
+  k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(d_solid, n_img, nx, ny, C, P.rel_residual * P.rel_residual, P.flux_balance,
+                                         (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, codes,
+                                         d_T_out, res, counter);
+  KB_LAUNCHED();
+  KB_CUDA(cudaGetLastError());
+  KB_CUDA(cudaEventRecord(c.ev1, c.st));
+  std::vector<BatchOut> h(n_img);
+  KB_CUDA(cudaMemcpyAsync(h.data(), res, (size_t)n_img * sizeof(BatchOut), cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  float ms = 0;
+  KB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  for (int i = 0; i < n_img; i++) {
+    keffb200_result& o = out[i];
+    o.q_left = h[i].ql;
+    o.q_right = h[i].qr;
+    o.keff = (h[i].ql + h[i].qr) / 2 / (P.tr - P.tl);
+    o.rel_residual = h[i].bb > 0 ? sqrt(h[i].rr / h[i].bb) : 0.0;
+    o.energy_residual = h[i].r1;
+    o.iters = (long)h[i].it;
+    o.status = h[i].status;
+    o.gpu_ms = ms;  // whole-batch device time
+  }
+  return 0;
+}
+
+}  // namespace kb

@@ -1,0 +1,357 @@
+// kernels.cuh -- device kernels of the grid solver (2D images are nz == 1 volumes).
+//
+// Data layout in HBM: every field is double[nz(+2 halo planes)][ny][nx], x fastest -- the
+// reference's index z*ny*nx + y*nx + x (Keff3D/keff3D.h:691).  The structure is one "code" byte per
+// cell (common.cuh).  Nothing else is stored: no coefficient matrix, no right-hand side.
+#pragma once
+#include "common.cuh"
+
+namespace kb {
+
+// ------------------------------------------------------------------------------------------------
+// structure -> code bytes.  Replaces the phase->k maps (Keff2D/keff2D.cpp:108-121,
+// Keff3D/keff3D.cpp:105-120) and the harmonic-mean selection inside DiscretizeMatrixCD2D/3D.
+// m points at local plane 0; planes -1 and nz are readable when lo/hi are set (slab neighbours).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_make_code(const uint8_t* __restrict__ m, uint8_t* __restrict__ code, Dom D, int lo, int hi) {
+  const long plane = (long)D.nx * D.ny, n = plane * D.nz;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % D.nx);
+    const long t = i / D.nx;
+    const int y = (int)(t % D.ny), z = (int)(t / D.ny);
+    const unsigned me = m[i] == 1;
+    unsigned c = me;
+    if (x > 0 && (unsigned)(m[i - 1] == 1) != me) c |= C_W;
+    if (x < D.nx - 1 && (unsigned)(m[i + 1] == 1) != me) c |= C_E;
+    if (y < D.ny - 1 && (unsigned)(m[i + D.nx] == 1) != me) c |= C_S;
+    if (y > 0 && (unsigned)(m[i - D.nx] == 1) != me) c |= C_N;
+    if ((z > 0 || lo) && (unsigned)(m[i - plane] == 1) != me) c |= C_F;
+    if ((z < D.nz - 1 || hi) && (unsigned)(m[i + plane] == 1) != me) c |= C_B;
+    code[i] = (uint8_t)c;
+  }
+}
+
+// Initial field: linear ramp between the wall temperatures evaluated at the cell centres, or the
+// constant TL the reference actually starts from (SolInitLinear, Keff2D/keff2D.h:584-611, whose
+// integer division collapses the ramp).
+__global__ void k_init_field(double* __restrict__ T, Dom D, double tl, double tr, int constant) {
+  const long n = (long)D.nx * D.ny * D.nz;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % D.nx);
+    T[i] = constant ? tl : tl + (tr - tl) * ((x + 0.5) / D.nx);
+  }
+}
+
+enum { MODE_APPLY = 0, MODE_INIT = 1, MODE_RESID = 2 };
+// MODE_APPLY: o0 = A*in,              partials {in.A in, -, -}
+// MODE_INIT : o0 = r = b - A*in, o1 = p = r/a_P, partials {r.z, r.r, b.b}
+// MODE_RESID: no output,              partials {-, r.r, sum|r|}
+
+template <int MODE>
+__device__ __forceinline__ void cell_epilogue(const Coef& C, unsigned c, bool x0, bool x1, const Faces& F,
+                                              double pc, double q, double& out0, double& out1, double* acc) {
+  if (MODE == MODE_APPLY) {
+    out0 = q;
+    acc[0] += pc * q;
+  } else {
+    const double b = rhs_of(C, c, x0, x1);
+    const double r = b - q;
+    if (MODE == MODE_INIT) {
+      const double z = r / F.diag;
+      out0 = r;
+      out1 = z;
+      acc[0] += r * z;
+      acc[1] += r * r;
+      acc[2] += b * b;
+    } else {
+      acc[1] += r * r;
+      acc[2] += fabs(r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain stencil kernel (any nx): rows are distributed round-robin over a fixed grid, neighbours are
+// read through L1/L2.  Fallback for odd nx and cross-check for the TMA kernel.
+// in/o0/o1 point at local plane 0; `in` has readable halo planes.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_stencil_plain(const double* __restrict__ in, const uint8_t* __restrict__ code,
+                                                       double* __restrict__ o0, double* __restrict__ o1, const Coef C,
+                                                       const Dom D, const Scal* __restrict__ S,
+                                                       double* __restrict__ partials) {
+  __shared__ double red[32 * 3];
+  if (S->done) return;
+  const long plane = (long)D.nx * D.ny;
+  const long rows = (long)D.ny * D.nz;
+  double acc[3] = {0, 0, 0};
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % D.ny), z = (int)(row / D.ny);
+    const bool y0 = y == 0, y1 = y == D.ny - 1, z0 = D.z0 + z == 0, z1 = D.z0 + z == D.nzg - 1;
+    const long base = row * D.nx;
+    for (int x = threadIdx.x; x < D.nx; x += blockDim.x) {
+      const long i = base + x;
+      const bool x0 = x == 0, x1 = x == D.nx - 1;
+      const unsigned c = code[i];
+      const Faces F = faces_of(C, c, x0, x1, y0, y1, z0, z1);
+      const double pc = in[i];
+      double q = F.diag * pc;
+      if (!x0) q -= F.w * in[i - 1];
+      if (!x1) q -= F.e * in[i + 1];
+      if (!y0) q -= F.n * in[i - D.nx];
+      if (!y1) q -= F.s * in[i + D.nx];
+      if (!z0) q -= F.f * in[i - plane];
+      if (!z1) q -= F.b * in[i + plane];
+      double a = 0, b2 = 0;
+      cell_epilogue<MODE>(C, c, x0, x1, F, pc, q, a, b2, acc);
+      if (MODE != MODE_RESID) o0[i] = a;
+      if (MODE == MODE_INIT) o1[i] = b2;
+    }
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA stencil kernel (nx even).  Work item = (64 x 8) xy tile x one z chunk.  A CTA marches its item
+// in z: planes (with a 2-cell x halo and 1-row y halo, zero-filled outside the domain by the TMA
+// unit) stream into an NST-deep shared-memory ring via cp.async.bulk.tensor + mbarrier; each thread
+// owns two x-adjacent cells and keeps their z-1 / z / z+1 values in registers, so every field value
+// is fetched from L2/HBM once per tile and read from shared memory ~3.5 times.
+// Items are dealt round-robin to a fixed grid (deterministic partial sums).
+// ------------------------------------------------------------------------------------------------
+constexpr int TX = 64, TY = 8, BOXW = TX + 4, BOXH = TY + 2, NST = 4, NTHR = 256;
+constexpr int STAGE_BYTES = BOXW * BOXH * 8;
+constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+
+struct Plan {
+  int ntx, nty, nzc, zlen, nitems;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CUtensorMap tm,
+                                                      const uint8_t* __restrict__ code, double* __restrict__ o0,
+                                                      double* __restrict__ o1, const Coef C, const Dom D, const Plan P,
+                                                      const Scal* __restrict__ S, double* __restrict__ partials) {
+  __shared__ __align__(128) unsigned char tiles[NST * STAGE_STRIDE];
+  __shared__ __align__(8) uint64_t full[NST];
+  __shared__ double red[32 * 3];
+  if (S->done) return;
+  const int tid = threadIdx.x, lx = (tid & 31) * 2, ly = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  uint32_t seq = 0;  // planes streamed so far by this CTA (identical in every thread)
+  double acc[3] = {0, 0, 0};
+  const long plane = (long)D.nx * D.ny;
+
+  for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+    const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+    const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
+    const int len = min(D.nz, zb + P.zlen) - zb, nplanes = len + 2;
+    const int gx = xo + lx, gy = yo + ly;
+    const bool active = gx < D.nx && gy < D.ny;
+    const bool y0 = gy == 0, y1 = gy == D.ny - 1;
+    const bool ax0 = gx == 0, bx1 = gx + 1 == D.nx - 1;
+
+    __syncthreads();  // ring is idle (previous item fully consumed; barriers initialised)
+    if (tid == 0) {
+      const int npre = min(NST, nplanes);
+      for (int k = 0; k < npre; k++) {
+        const uint32_t st = (seq + k) % NST;
+        mbar_expect_tx(&full[st], STAGE_BYTES);
+        // tensor z index = local plane + 1 (field arrays carry one halo plane below plane 0)
+        tma_load_3d(tiles + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + k);
+      }
+    }
+    const int coff = (ly + 1) * BOXW + lx + 2;  // my cell pair inside a staged plane
+    double2 pm, pc, pp;
+    {
+      const uint32_t s0 = seq % NST, s1 = (seq + 1) % NST;
+      mbar_wait(&full[s0], (seq / NST) & 1);
+      pm = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s0 * STAGE_STRIDE) + coff);
+      mbar_wait(&full[s1], ((seq + 1) / NST) & 1);
+      pc = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s1 * STAGE_STRIDE) + coff);
+    }
+    long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of my first cell in plane zb
+    unsigned cnext = active ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
+
+    for (int k = 1; k <= len; k++) {
+      const int lz = zb + k - 1;
+      __syncthreads();  // every thread is done with plane k-1's stage
+      if (tid == 0 && k - 1 + NST < nplanes) {
+        const uint32_t st = (seq + k - 1) % NST;  // == stage of plane k-1+NST
+        mbar_expect_tx(&full[st], STAGE_BYTES);
+        tma_load_3d(tiles + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + k - 1 + NST);
+      }
+      const uint32_t sc = (seq + k) % NST, sn = (seq + k + 1) % NST;
+      mbar_wait(&full[sn], ((seq + k + 1) / NST) & 1);
+      const double* cur = reinterpret_cast<const double*>(tiles + sc * STAGE_STRIDE);
+      pp = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + sn * STAGE_STRIDE) + coff);
+      const unsigned cc = cnext;
+      if (active && k < len) cnext = *reinterpret_cast<const unsigned short*>(code + ci + plane);
+      if (active) {
+        const double2 pn = *reinterpret_cast<const double2*>(cur + coff - BOXW);
+        const double2 ps = *reinterpret_cast<const double2*>(cur + coff + BOXW);
+        const double pw = cur[coff - 1], pe = cur[coff + 2];
+        const bool z0 = D.z0 + lz == 0, z1 = D.z0 + lz == D.nzg - 1;
+        const unsigned ca = cc & 0xffu, cb = cc >> 8;
+        const Faces Fa = faces_of(C, ca, ax0, false, y0, y1, z0, z1);
+        const Faces Fb = faces_of(C, cb, false, bx1, y0, y1, z0, z1);
+        const double qa = Fa.diag * pc.x - Fa.w * pw - Fa.e * pc.y - Fa.n * pn.x - Fa.s * ps.x - Fa.f * pm.x -
+                          Fa.b * pp.x;
+        const double qb = Fb.diag * pc.y - Fb.w * pc.x - Fb.e * pe - Fb.n * pn.y - Fb.s * ps.y - Fb.f * pm.y -
+                          Fb.b * pp.y;
+        double2 u, v;
+        cell_epilogue<MODE>(C, ca, ax0, false, Fa, pc.x, qa, u.x, v.x, acc);
+        cell_epilogue<MODE>(C, cb, false, bx1, Fb, pc.y, qb, u.y, v.y, acc);
+        if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci) = u;
+        if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci) = v;
+      }
+      pm = pc;
+      pc = pp;
+      ci += plane;
+    }
+    seq += nplanes;
+  }
+  block_sum<3>(acc, red);
+  if (tid == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CG vector kernels.  Rows round-robin over a fixed grid; a_P is recomputed from the code byte.
+//   k_cg_update : alpha = r.z / p.q;  x += alpha p;  r -= alpha q;  partials {r.(r/a_P), r.r}
+//   k_cg_dir    : beta = r.z_new / r.z_old;  p = r/a_P + beta p
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, double* __restrict__ r,
+                                                   const double* __restrict__ p, const double* __restrict__ q,
+                                                   const uint8_t* __restrict__ code, const Coef C, const Dom D,
+                                                   const Scal* __restrict__ S, int par,
+                                                   double* __restrict__ partials) {
+  __shared__ double red[32 * 2];
+  if (S->done) return;
+  const double alpha = S->rz[par] / S->pq;
+  const long rows = (long)D.ny * D.nz;
+  double acc[2] = {0, 0};
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % D.ny), z = (int)(row / D.ny);
+    const bool y0 = y == 0, y1 = y == D.ny - 1, z0 = D.z0 + z == 0, z1 = D.z0 + z == D.nzg - 1;
+    const long base = row * D.nx;
+    for (int xx = threadIdx.x; xx < D.nx; xx += blockDim.x) {
+      const long i = base + xx;
+      const double d = diag_of(C, code[i], xx == 0, xx == D.nx - 1, y0, y1, z0, z1);
+      const double pi = p[i], qi = q[i];
+      x[i] += alpha * pi;
+      const double ri = r[i] - alpha * qi;
+      r[i] = ri;
+      acc[0] += ri * (ri / d);
+      acc[1] += ri * ri;
+    }
+  }
+  block_sum<2>(acc, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 2 + 0] = acc[0];
+    partials[blockIdx.x * 2 + 1] = acc[1];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cg_dir(double* __restrict__ p, const double* __restrict__ r,
+                                                const uint8_t* __restrict__ code, const Coef C, const Dom D,
+                                                const Scal* __restrict__ S, int par) {
+  if (S->done) return;
+  const double beta = S->rz[par ^ 1] / S->rz[par];
+  const long rows = (long)D.ny * D.nz;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % D.ny), z = (int)(row / D.ny);
+    const bool y0 = y == 0, y1 = y == D.ny - 1, z0 = D.z0 + z == 0, z1 = D.z0 + z == D.nzg - 1;
+    const long base = row * D.nx;
+    for (int xx = threadIdx.x; xx < D.nx; xx += blockDim.x) {
+      const long i = base + xx;
+      const double d = diag_of(C, code[i], xx == 0, xx == D.nx - 1, y0, y1, z0, z1);
+      p[i] = r[i] / d + beta * p[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-block finalizers: deterministic sums of per-CTA partials + the scalar recurrences
+// ------------------------------------------------------------------------------------------------
+// what: 0 -> p.q (stride 3, slot 0) into S->pq
+//       1 -> {r.z, r.r} (stride 2) into S->tmp[0..1]
+//       2 -> INIT {r.z, r.r, b.b} (stride 3) into S->tmp[0..2]
+//       3 -> RESID {-, r.r, |r|1} (stride 3) into S->tmp[1..2]
+//       4 -> flux {QL, QR} (stride 2) into S->tmp[0..1]
+__global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int n, int what, Scal* S) {
+  __shared__ double red[32 * 3];
+  if (S->done && what <= 1) return;
+  const int stride = (what == 1 || what == 4) ? 2 : 3;
+  double acc[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    acc[0] += partials[i * stride];
+    acc[1] += partials[i * stride + 1];
+    if (stride == 3) acc[2] += partials[i * stride + 2];
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    if (what == 0) S->pq = acc[0];
+    else if (what == 3) { S->tmp[1] = acc[1]; S->tmp[2] = acc[2]; }
+    else { S->tmp[0] = acc[0]; S->tmp[1] = acc[1]; S->tmp[2] = acc[2]; }
+  }
+}
+
+// scalar steps (run after the optional all-reduce of S->tmp)
+__global__ void k_step_init(Scal* S) {
+  S->rz[0] = S->tmp[0];
+  S->rr = S->tmp[1];
+  S->bb = S->tmp[2];
+  S->it = 0;
+  S->done = !(S->tmp[1] > S->thr2 * S->tmp[2]);
+}
+__global__ void k_step_iter(Scal* S, int par) {
+  if (S->done) return;
+  S->rz[par ^ 1] = S->tmp[0];
+  S->rr = S->tmp[1];
+  S->it += 1;
+  if (!(S->tmp[1] > S->thr2 * S->bb)) S->done = 1;
+}
+__global__ void k_step_flux(Scal* S) {
+  S->ql = S->tmp[0];
+  S->qr = S->tmp[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary-flux integration: QL = sum c_wall (T(x=0) - TL), QR = sum c_wall (TR - T(x=nx-1))
+// (Keff2D/keff2D.cpp:151-170, Keff3D/keff3D.cpp:145-163).  One thread per (z,y) row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_flux(const double* __restrict__ T, const uint8_t* __restrict__ code,
+                                              const Coef C, const Dom D, double* __restrict__ qL,
+                                              double* __restrict__ qR, double* __restrict__ partials) {
+  __shared__ double red[32 * 2];
+  const long rows = (long)D.ny * D.nz;
+  double acc[2] = {0, 0};
+  for (long row = blockIdx.x * (long)blockDim.x + threadIdx.x; row < rows; row += (long)gridDim.x * blockDim.x) {
+    const long l = row * D.nx, e = l + D.nx - 1;
+    const double a = ((code[l] & C_PH) ? C.wall[1] : C.wall[0]) * (T[l] - C.tl);
+    const double b = ((code[e] & C_PH) ? C.wall[1] : C.wall[0]) * (C.tr - T[e]);
+    if (qL) qL[row] = a;
+    if (qR) qR[row] = b;
+    acc[0] += a;
+    acc[1] += b;
+  }
+  block_sum<2>(acc, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 2 + 0] = acc[0];
+    partials[blockIdx.x * 2 + 1] = acc[1];
+  }
+}
+
+}  // namespace kb

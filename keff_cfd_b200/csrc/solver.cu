@@ -1,0 +1,699 @@
+// solver.cu -- host driver of the grid solver (diagonally preconditioned CG on the matrix-free
+// finite-volume operator), the z-slab multi-process variant, and the extern "C" ABI.
+//
+// Replaces, per solve: DiscretizeMatrixCD2D/3D + SolInitLinear + ParallelGS/SerialGS/ParallelGS3D
+// + the flux loops of main() (Keff2D/keff2D.cpp:131-170, Keff3D/keff3D.cpp:134-163) and
+// JacobiGPU (Keff2DGPU/keff2D.cuh:726-849).  All convergence control is on the device; the host
+// only reads a 150-byte scalar record every `check_every` iterations.
+#include "context.cuh"
+#include "kernels.cuh"
+
+namespace kb {
+
+// batch2d.cu
+int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params& P, double* d_T_out,
+                      keffb200_result* out);
+
+static keffb200_params norm_params(const keffb200_params* p) {
+  keffb200_params P;
+  if (p) P = *p; else keffb200_default_params(&P);
+  if (!(P.rel_residual > 0)) P.rel_residual = 1e-8;
+  if (!(P.flux_balance > 0)) P.flux_balance = 1e-6;
+  if (P.check_every <= 0) P.check_every = 32;
+  if (P.max_iter <= 0) P.max_iter = 500000;
+  if (!(P.convergence > 0)) P.convergence = 1e-5;
+  return P;
+}
+
+Coef make_coef(int nx, int ny, int nzg, const keffb200_params& P) {
+  // face conductances in the reference's own operation order (Keff3D/keff3D.h:698-757; with
+  // dz = 1 they reduce to the 2D expressions of Keff2D/keff2D.h:529-577)
+  const double dx = 1.0 / nx, dy = 1.0 / ny, dz = nzg > 1 ? 1.0 / nzg : 1.0;
+  const double k[2] = {P.kf, P.ks};
+  auto hmean = [](double w, double a, double b) { return (w + w) / (w / a + w / b); };
+  Coef C;
+  for (int ph = 0; ph < 2; ph++) {
+    C.same[0][ph] = k[ph] * dy * dz / dx;
+    C.same[1][ph] = k[ph] * dx * dz / dy;
+    C.same[2][ph] = k[ph] * dy * dx / dz;
+    C.wall[ph] = k[ph] * dy * dz / (dx / 2);
+  }
+  C.diff[0] = hmean(dx / 2, P.ks, P.kf) * dy * dz / dx;
+  C.diff[1] = hmean(dy / 2, P.ks, P.kf) * dx * dz / dy;
+  C.diff[2] = hmean(dz / 2, P.ks, P.kf) * dy * dx / dz;
+  C.tl = P.tl;
+  C.tr = P.tr;
+  return C;
+}
+
+static int ensure_ws(const Dom& D) {
+  Ctx& c = ctx();
+  const size_t plane = (size_t)D.nx * D.ny, need = plane * (D.nz + 2);
+  if (need > c.cap_field) {
+    for (double** f : {&c.x, &c.r, &c.p, &c.q}) {
+      if (*f) cudaFree(*f);
+      *f = nullptr;
+    }
+    if (c.code) cudaFree(c.code);
+    if (c.mask) cudaFree(c.mask);
+    c.code = c.mask = nullptr;
+    c.cap_field = 0;
+    for (double** f : {&c.x, &c.r, &c.p, &c.q}) KB_CUDA(cudaMalloc(f, need * sizeof(double)));
+    KB_CUDA(cudaMalloc(&c.code, need));
+    KB_CUDA(cudaMalloc(&c.mask, need));
+    c.cap_field = need;
+  }
+  const size_t rows = (size_t)D.ny * D.nz;
+  if (rows > c.cap_aux) {
+    if (c.qL) cudaFree(c.qL);
+    if (c.qR) cudaFree(c.qR);
+    c.qL = c.qR = nullptr;
+    c.cap_aux = 0;
+    KB_CUDA(cudaMalloc(&c.qL, rows * sizeof(double)));
+    KB_CUDA(cudaMalloc(&c.qR, rows * sizeof(double)));
+    c.cap_aux = rows;
+  }
+  return 0;
+}
+
+// ---- NCCL helpers (no-ops when world == 1) -----------------------------------------------------
+static int nccl_check(int rc, const char* what) {
+  if (rc == 0) return 0;
+  Nccl& n = ctx().nccl;
+  return fail(KEFFB200_ENCCL, "%s: %s", what, n.GetErrorString ? n.GetErrorString(rc) : "nccl error");
+}
+
+static int allreduce_tmp(double* dptr, int count) {
+  Nccl& n = ctx().nccl;
+  if (n.world <= 1 || !n.comm) return 0;
+  return nccl_check(n.AllReduce(dptr, dptr, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, n.comm, ctx().st), "ncclAllReduce");
+}
+
+// exchange the boundary planes of a halo'ed field with the z neighbours (f points at the halo plane)
+static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
+  Nccl& n = ctx().nccl;
+  if (n.world <= 1 || !n.comm) return 0;
+  const size_t plane = (size_t)D.nx * D.ny;
+  double* lo_halo = f_halo;
+  double* first = f_halo + plane;
+  double* last = f_halo + plane * D.nz;
+  double* hi_halo = f_halo + plane * (D.nz + 1);
+  KB_TRY(nccl_check(n.GroupStart(), "ncclGroupStart"));
+  if (n.rank > 0) {
+    KB_TRY(nccl_check(n.Send(first, plane, 8, n.rank - 1, n.comm, st), "ncclSend"));
+    KB_TRY(nccl_check(n.Recv(lo_halo, plane, 8, n.rank - 1, n.comm, st), "ncclRecv"));
+  }
+  if (n.rank < n.world - 1) {
+    KB_TRY(nccl_check(n.Send(last, plane, 8, n.rank + 1, n.comm, st), "ncclSend"));
+    KB_TRY(nccl_check(n.Recv(hi_halo, plane, 8, n.rank + 1, n.comm, st), "ncclRecv"));
+  }
+  KB_TRY(nccl_check(n.GroupEnd(), "ncclGroupEnd"));
+  return 0;
+}
+
+// ---- stencil launcher ---------------------------------------------------------------------------
+struct Stencil {
+  bool tma = false;
+  Plan plan{};
+  int grid = 0;
+  Dom D{};
+  Coef C{};
+  CUtensorMap tm_x, tm_p;  // descriptors for the two fields that are ever stencil inputs
+};
+
+static int make_tmap(CUtensorMap* tm, double* field_halo, const Dom& D) {
+  Ctx& c = ctx();
+  cuuint64_t dims[3] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nz + 2};
+  cuuint64_t strides[2] = {(cuuint64_t)D.nx * 8, (cuuint64_t)D.nx * D.ny * 8};
+  cuuint32_t box[3] = {BOXW, BOXH, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = c.encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, field_halo, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(KEFFB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <int MODE>
+static int occupancy_tma() {
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stencil_tma<MODE>, NTHR, 0);
+  return std::max(occ, 1);
+}
+
+static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
+  Ctx& c = ctx();
+  s.D = D;
+  s.C = C;
+  s.tma = !(flags & KEFFB200_F_NO_TMA) && (D.nx % 2 == 0) && c.encode != nullptr;
+  if (s.tma) {
+    KB_TRY(make_tmap(&s.tm_x, c.x, D));
+    KB_TRY(make_tmap(&s.tm_p, c.p, D));
+    const int occ = occupancy_tma<MODE_APPLY>();
+    const int G = c.sms * occ;
+    Plan pl;
+    pl.ntx = (D.nx + TX - 1) / TX;
+    pl.nty = (D.ny + TY - 1) / TY;
+    const long tiles = (long)pl.ntx * pl.nty;
+    // choose the z chunking that minimises (items per CTA) x (planes streamed per item)
+    long best_cost = -1;
+    int best_nzc = 1;
+    for (int nzc = 1; nzc <= std::max(1, D.nz / 4); nzc++) {
+      const int zlen = (D.nz + nzc - 1) / nzc;
+      const int real_nzc = (D.nz + zlen - 1) / zlen;
+      const long items = tiles * real_nzc;
+      const long per_cta = (items + G - 1) / G;
+      const long cost = per_cta * (zlen + 2 + 6);  // +6: per-item pipeline fill/drain
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_nzc = real_nzc;
+      }
+    }
+    pl.zlen = (D.nz + best_nzc - 1) / best_nzc;
+    pl.nzc = (D.nz + pl.zlen - 1) / pl.zlen;
+    pl.nitems = (int)(tiles * pl.nzc);
+    s.plan = pl;
+    s.grid = (int)std::min<long>(pl.nitems, G);
+  } else {
+    const long rows = (long)D.ny * D.nz;
+    s.grid = (int)std::min<long>(rows, (long)c.sms * 8);
+  }
+  if (s.grid > PARTIAL_SLOTS) s.grid = PARTIAL_SLOTS;
+  return 0;
+}
+
+// in_halo: halo'ed field base; which: 0 -> x, 1 -> p (selects the tensor map)
+template <int MODE>
+static int stencil_launch(const Stencil& s, int which, double* o0, double* o1) {
+  Ctx& c = ctx();
+  const size_t plane = (size_t)s.D.nx * s.D.ny;
+  double* in_halo = which == 0 ? c.x : c.p;
+  if (s.tma) {
+    k_stencil_tma<MODE><<<s.grid, NTHR, 0, c.st>>>(which == 0 ? s.tm_x : s.tm_p, c.code, o0, o1, s.C, s.D, s.plan, c.S,
+                                                    c.partials);
+  } else {
+    k_stencil_plain<MODE><<<s.grid, 256, 0, c.st>>>(in_halo + plane, c.code, o0, o1, s.C, s.D, c.S, c.partials);
+  }
+  KB_LAUNCHED();
+  KB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int vec_threads(int nx) { return std::min(256, std::max(32, (nx + 31) / 32 * 32)); }
+
+// ---- the solve ----------------------------------------------------------------------------------
+// d_mask_halo: (nz+2) planes (plane 0 and nz+1 are the slab neighbours' planes or don't-care);
+// d_Tinit / d_Tout: nz planes, nullable.
+static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_params& P, const double* d_Tinit,
+                      double* d_Tout, double* d_qL, double* d_qR, keffb200_result* out) {
+  Ctx& c = ctx();
+  Nccl& nc = c.nccl;
+  if (D.nx < 2 || D.ny < 1 || D.nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", D.nx, D.ny, D.nz);
+  if (P.tr == P.tl) return fail(KEFFB200_EINVAL, "TR == TL: Keff undefined");
+  if (!(P.ks > 0) || !(P.kf > 0)) return fail(KEFFB200_EINVAL, "conductivities must be positive");
+  KB_TRY(ensure_ws(D));
+  const size_t plane = (size_t)D.nx * D.ny, n = plane * D.nz;
+  const Coef C = make_coef(D.nx, D.ny, D.nzg, P);
+  const bool lo = nc.world > 1 && D.z0 > 0, hi = nc.world > 1 && D.z0 + D.nz < D.nzg;
+  double *x = c.x + plane, *r = c.r + plane, *p = c.p + plane, *q = c.q + plane;
+  const int vt = vec_threads(D.nx);
+  const long rows = (long)D.ny * D.nz;
+  const int gv = (int)std::min<long>(rows, (long)c.sms * (2048 / vt));
+  const int gf = (int)std::min<long>((rows + 255) / 256, (long)c.sms * 4);
+
+  KB_CUDA(cudaEventRecord(c.ev0, c.st));
+  k_make_code<<<c.sms * 8, 256, 0, c.st>>>(d_mask_halo + plane, c.code, D, lo, hi);
+  KB_LAUNCHED();
+  // halo planes of the two stencil inputs start at zero (global ends keep them: zero coefficient)
+  KB_CUDA(cudaMemsetAsync(c.x, 0, plane * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.x + plane * (D.nz + 1), 0, plane * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.p, 0, plane * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.p + plane * (D.nz + 1), 0, plane * 8, c.st));
+  if (d_Tinit) {
+    KB_CUDA(cudaMemcpyAsync(x, d_Tinit, n * 8, cudaMemcpyDeviceToDevice, c.st));
+  } else {
+    k_init_field<<<c.sms * 8, 256, 0, c.st>>>(x, D, P.tl, P.tr, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0);
+    KB_LAUNCHED();
+  }
+  Stencil s;
+  KB_TRY(stencil_setup(s, D, C, P.flags));
+
+  Scal h0;
+  memset(&h0, 0, sizeof h0);
+  double thr = P.rel_residual;
+  h0.thr2 = thr * thr;
+  *c.hS = h0;
+  KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
+
+  long total_iters = 0;
+  double keff_prev = NAN, keff = NAN, ql = 0, qr = 0;
+  int status = 1;
+  bool need_init = true;
+  long k = 0;  // host-side iteration index since the last (re)start
+  while (true) {
+    if (need_init) {
+      KB_TRY(exchange_halo(c.x, D, c.st));
+      KB_TRY(stencil_launch<MODE_INIT>(s, 0, r, p));
+      k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 2, c.S);
+      KB_LAUNCHED();
+      KB_TRY(allreduce_tmp(c.S->tmp, 3));
+      k_step_init<<<1, 1, 0, c.st>>>(c.S);
+      KB_LAUNCHED();
+      need_init = false;
+      k = 0;
+    }
+    const long batch = std::min<long>(P.check_every, P.max_iter - total_iters - k);
+    for (long i = 0; i < batch; i++, k++) {
+      const int par = (int)(k & 1);
+      KB_TRY(exchange_halo(c.p, D, c.st));
+      KB_TRY(stencil_launch<MODE_APPLY>(s, 1, q, nullptr));
+      k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 0, c.S);
+      KB_LAUNCHED();
+      KB_TRY(allreduce_tmp(&c.S->pq, 1));
+      k_cg_update<<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
+      KB_LAUNCHED();
+      k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gv, 1, c.S);
+      KB_LAUNCHED();
+      KB_TRY(allreduce_tmp(c.S->tmp, 2));
+      k_step_iter<<<1, 1, 0, c.st>>>(c.S, par);
+      KB_LAUNCHED();
+      k_cg_dir<<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
+      KB_LAUNCHED();
+    }
+    // host-visible check: flux, Keff, flags
+    k_flux<<<gf, 256, 0, c.st>>>(x, c.code, C, D, nullptr, nullptr, c.partials);
+    KB_LAUNCHED();
+    k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gf, 4, c.S);
+    KB_LAUNCHED();
+    KB_TRY(allreduce_tmp(c.S->tmp, 2));
+    k_step_flux<<<1, 1, 0, c.st>>>(c.S);
+    KB_LAUNCHED();
+    KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
+    KB_CUDA(cudaStreamSynchronize(c.st));
+    ql = c.hS->ql;
+    qr = c.hS->qr;
+    keff = (ql + qr) / 2 / (P.tr - P.tl);
+    const double imb = fabs(ql - qr) / fabs(keff);
+    // field is frozen once `done` is set, so the reference's "Keff change between checks" is 0 then
+    const double dk = c.hS->done ? 0.0 : fabs((keff - keff_prev) / keff_prev);
+    keff_prev = keff;
+    const long its_now = total_iters + c.hS->it;
+    if (!std::isfinite(keff)) return fail(KEFFB200_ECUDA, "solver produced a non-finite Keff");
+    if (c.hS->done) {
+      if ((imb <= P.flux_balance && dk <= P.convergence) || thr < 1e-14) {
+        status = 0;
+        total_iters = its_now;
+        break;
+      }
+      // residual target met but the two wall fluxes still disagree: tighten and restart CG from x
+      thr *= 0.01;
+      total_iters = its_now;
+      c.hS->thr2 = thr * thr;
+      c.hS->done = 0;
+      KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
+      need_init = true;
+      if (total_iters >= P.max_iter) break;
+      continue;
+    }
+    if (its_now >= P.max_iter) {
+      total_iters = its_now;
+      break;
+    }
+  }
+
+  // true residual of the returned field, per-row fluxes, outputs
+  KB_CUDA(cudaMemsetAsync(&c.S->done, 0, sizeof(int), c.st));
+  KB_TRY(exchange_halo(c.x, D, c.st));
+  KB_TRY(stencil_launch<MODE_RESID>(s, 0, nullptr, nullptr));
+  k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 3, c.S);
+  KB_LAUNCHED();
+  KB_TRY(allreduce_tmp(c.S->tmp, 3));
+  KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
+  if (d_qL || d_qR) {
+    k_flux<<<gf, 256, 0, c.st>>>(x, c.code, C, D, d_qL, d_qR, c.partials);
+    KB_LAUNCHED();
+  }
+  if (d_Tout) KB_CUDA(cudaMemcpyAsync(d_Tout, x, n * 8, cudaMemcpyDeviceToDevice, c.st));
+  KB_CUDA(cudaEventRecord(c.ev1, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  float ms = 0;
+  KB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  if (out) {
+    out->keff = keff;
+    out->q_left = ql;
+    out->q_right = qr;
+    out->rel_residual = c.hS->bb > 0 ? sqrt(c.hS->tmp[1] / c.hS->bb) : 0.0;
+    out->energy_residual = c.hS->tmp[2];
+    out->iters = total_iters;
+    out->status = status;
+    out->gpu_ms = ms;
+  }
+  return 0;
+}
+
+// stage a host (or device) structure into the halo'ed mask buffer of the workspace
+static int stage_mask(const uint8_t* src, bool src_is_device, const Dom& D) {
+  Ctx& c = ctx();
+  KB_TRY(ensure_ws(D));
+  const size_t plane = (size_t)D.nx * D.ny;
+  KB_CUDA(cudaMemsetAsync(c.mask, 0, plane, c.st));
+  KB_CUDA(cudaMemsetAsync(c.mask + plane * (D.nz + 1), 0, plane, c.st));
+  KB_CUDA(cudaMemcpyAsync(c.mask + plane, src, plane * D.nz,
+                          src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.st));
+  return 0;
+}
+
+static int need_ready() {
+  if (!ctx().ready) return fail(KEFFB200_ESTATE, "keffb200_init has not been called");
+  return 0;
+}
+
+}  // namespace kb
+
+using namespace kb;
+
+extern "C" {
+
+const char* keffb200_version(void) { return "keffb200 0.1 (sm_100a)"; }
+const char* keffb200_last_error(void) { return ctx().err.c_str(); }
+long keffb200_launch_count(void) { return ctx().launches; }
+
+void keffb200_default_params(keffb200_params* p) {
+  memset(p, 0, sizeof *p);
+  p->ks = 10;
+  p->kf = 1;
+  p->tl = 0;
+  p->tr = 1;
+  p->convergence = 1e-5;
+  p->max_iter = 500000;
+  p->rel_residual = 1e-8;
+  p->flux_balance = 1e-6;
+  p->check_every = 32;
+  p->flags = 0;
+}
+
+int keffb200_init(int device) {
+  Ctx& c = ctx();
+  if (c.ready && c.device == device) return 0;
+  if (c.ready) keffb200_shutdown();
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(KEFFB200_ENOGPU, "no CUDA device visible: this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(KEFFB200_EINVAL, "device %d out of range (%d visible)", device, ndev);
+  KB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(KEFFB200_ENOGPU, "device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major,
+                prop.minor);
+  c.device = device;
+  c.sms = prop.multiProcessorCount;
+  KB_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+  KB_CUDA(cudaStreamCreateWithFlags(&c.st2, cudaStreamNonBlocking));
+  KB_CUDA(cudaEventCreate(&c.ev0));
+  KB_CUDA(cudaEventCreate(&c.ev1));
+  KB_CUDA(cudaEventCreateWithFlags(&c.evx, cudaEventDisableTiming));
+  KB_CUDA(cudaEventCreateWithFlags(&c.evy, cudaEventDisableTiming));
+  KB_CUDA(cudaMalloc(&c.partials, (size_t)PARTIAL_SLOTS * 3 * sizeof(double)));
+  KB_CUDA(cudaMalloc(&c.S, sizeof(Scal)));
+  KB_CUDA(cudaMallocHost(&c.hS, sizeof(Scal)));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+      qr == cudaDriverEntryPointSuccess)
+    c.encode = (PFN_encodeTiled)fn;
+  else
+    return fail(KEFFB200_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+  c.launches = 0;
+  c.ready = true;
+  return 0;
+}
+
+void keffb200_shutdown(void) {
+  Ctx& c = ctx();
+  if (!c.ready) return;
+  keffb200_dist_shutdown();
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  for (double** f : {&c.x, &c.r, &c.p, &c.q, &c.qL, &c.qR, &c.partials}) {
+    if (*f) cudaFree(*f);
+    *f = nullptr;
+  }
+  if (c.code) cudaFree(c.code);
+  if (c.mask) cudaFree(c.mask);
+  if (c.batch_ws) cudaFree(c.batch_ws);
+  if (c.S) cudaFree(c.S);
+  if (c.hS) cudaFreeHost(c.hS);
+  c.code = c.mask = nullptr;
+  c.batch_ws = nullptr;
+  c.S = c.hS = nullptr;
+  c.cap_field = c.cap_aux = c.cap_batch = 0;
+  cudaEventDestroy(c.ev0);
+  cudaEventDestroy(c.ev1);
+  cudaEventDestroy(c.evx);
+  cudaEventDestroy(c.evy);
+  cudaStreamDestroy(c.st);
+  cudaStreamDestroy(c.st2);
+  c.ready = false;
+}
+
+int keffb200_solve3d(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T_init,
+                     double* T_out, double* qL, double* qR, keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!solid || !out) return fail(KEFFB200_EINVAL, "null argument");
+  Ctx& c = ctx();
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz, 0, nz};
+  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
+  KB_TRY(stage_mask(solid, false, D));
+  const size_t n = (size_t)nx * ny * nz;
+  double* dT = nullptr;
+  if (T_init) {
+    // q is free until the first iteration: use it to stage the warm start
+    dT = c.q + (size_t)nx * ny;
+    KB_CUDA(cudaMemcpyAsync(dT, T_init, n * 8, cudaMemcpyHostToDevice, c.st));
+  }
+  KB_TRY(solve_grid(c.mask, D, P, dT, nullptr, qL ? c.qL : nullptr, qR ? c.qR : nullptr, out));
+  if (T_out) KB_CUDA(cudaMemcpyAsync(T_out, c.x + (size_t)nx * ny, n * 8, cudaMemcpyDeviceToHost, c.st));
+  const size_t rows = (size_t)ny * nz;
+  if (qL) KB_CUDA(cudaMemcpyAsync(qL, c.qL, rows * 8, cudaMemcpyDeviceToHost, c.st));
+  if (qR) KB_CUDA(cudaMemcpyAsync(qR, c.qR, rows * 8, cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  return 0;
+}
+
+int keffb200_solve2d(const uint8_t* solid, int nx, int ny, const keffb200_params* p, const double* T_init,
+                     double* T_out, double* qL, double* qR, keffb200_result* out) {
+  return keffb200_solve3d(solid, nx, ny, 1, p, T_init, T_out, qL, qR, out);
+}
+
+int keffb200_solve3d_dev(const uint8_t* d_solid, int nx, int ny, int nz, const keffb200_params* p,
+                         const double* d_T_init, double* d_T_out, keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!d_solid || !out) return fail(KEFFB200_EINVAL, "null argument");
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz, 0, nz};
+  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
+  KB_TRY(stage_mask(d_solid, true, D));
+  return solve_grid(ctx().mask, D, P, d_T_init, d_T_out, nullptr, nullptr, out);
+}
+
+int keffb200_solve3d_slab_dev(const uint8_t* d_solid_halo, int nx, int ny, int nz_local, int z0, int nz_global,
+                              const keffb200_params* p, double* d_T_out, keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!d_solid_halo || !out) return fail(KEFFB200_EINVAL, "null argument");
+  if (z0 < 0 || nz_local < 1 || z0 + nz_local > nz_global) return fail(KEFFB200_EINVAL, "bad slab extent");
+  if (ctx().nccl.world > 1 && !ctx().nccl.comm) return fail(KEFFB200_ESTATE, "keffb200_dist_init has not been called");
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz_local, z0, nz_global};
+  KB_TRY(ensure_ws(D));
+  return solve_grid(d_solid_halo, D, P, nullptr, d_T_out, nullptr, nullptr, out);
+}
+
+int keffb200_solve2d_batch_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params* p,
+                               double* d_T_out, keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!d_solid || !out || n_img < 1) return fail(KEFFB200_EINVAL, "bad argument");
+  return batch2d_solve_dev(d_solid, n_img, nx, ny, norm_params(p), d_T_out, out);
+}
+
+int keffb200_solve2d_batch(const uint8_t* solid, int n_img, int nx, int ny, const keffb200_params* p, double* T_out,
+                           keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!solid || !out || n_img < 1) return fail(KEFFB200_EINVAL, "bad argument");
+  Ctx& c = ctx();
+  const size_t n = (size_t)nx * ny, tot = n * n_img;
+  uint8_t* dm = nullptr;
+  double* dT = nullptr;
+  KB_CUDA(cudaMalloc(&dm, tot));
+  if (T_out && cudaMalloc(&dT, tot * 8) != cudaSuccess) {
+    cudaFree(dm);
+    return fail(KEFFB200_ENOMEM, "cannot allocate batch temperature output");
+  }
+  int rc = 0;
+  if (cudaMemcpyAsync(dm, solid, tot, cudaMemcpyHostToDevice, c.st) != cudaSuccess)
+    rc = fail(KEFFB200_ECUDA, "H2D copy of the image batch failed");
+  if (!rc) rc = batch2d_solve_dev(dm, n_img, nx, ny, norm_params(p), dT, out);
+  if (!rc && T_out) {
+    if (cudaMemcpyAsync(T_out, dT, tot * 8, cudaMemcpyDeviceToHost, c.st) != cudaSuccess ||
+        cudaStreamSynchronize(c.st) != cudaSuccess)
+      rc = fail(KEFFB200_ECUDA, "D2H copy of the temperature maps failed");
+  }
+  cudaFree(dm);
+  if (dT) cudaFree(dT);
+  return rc;
+}
+
+// ---- pieces ------------------------------------------------------------------------------------
+int keffb200_apply(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* xin,
+                   double* y, double* b) {
+  KB_TRY(need_ready());
+  if (!solid || !xin || !y) return fail(KEFFB200_EINVAL, "null argument");
+  Ctx& c = ctx();
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz, 0, nz};
+  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
+  KB_TRY(stage_mask(solid, false, D));
+  const size_t plane = (size_t)nx * ny, n = plane * nz;
+  const Coef C = make_coef(nx, ny, nz, P);
+  k_make_code<<<c.sms * 8, 256, 0, c.st>>>(c.mask + plane, c.code, D, 0, 0);
+  KB_LAUNCHED();
+  KB_CUDA(cudaMemsetAsync(c.p, 0, plane * (nz + 2) * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.x, 0, plane * (nz + 2) * 8, c.st));
+  KB_CUDA(cudaMemcpyAsync(c.p + plane, xin, n * 8, cudaMemcpyHostToDevice, c.st));
+  KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
+  Stencil s;
+  KB_TRY(stencil_setup(s, D, C, P.flags));
+  KB_TRY(stencil_launch<MODE_APPLY>(s, 1, c.q + plane, nullptr));
+  KB_CUDA(cudaMemcpyAsync(y, c.q + plane, n * 8, cudaMemcpyDeviceToHost, c.st));
+  if (b) {
+    // b = r of the INIT mode evaluated at x = 0
+    KB_TRY(stencil_launch<MODE_INIT>(s, 0, c.r + plane, c.q + plane));
+    KB_CUDA(cudaMemcpyAsync(b, c.r + plane, n * 8, cudaMemcpyDeviceToHost, c.st));
+  }
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  return 0;
+}
+
+int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T, double* qL,
+                  double* qR, keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!solid || !T || !out) return fail(KEFFB200_EINVAL, "null argument");
+  Ctx& c = ctx();
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz, 0, nz};
+  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
+  KB_TRY(stage_mask(solid, false, D));
+  const size_t plane = (size_t)nx * ny, n = plane * nz;
+  const long rows = (long)ny * nz;
+  const Coef C = make_coef(nx, ny, nz, P);
+  k_make_code<<<c.sms * 8, 256, 0, c.st>>>(c.mask + plane, c.code, D, 0, 0);
+  KB_LAUNCHED();
+  KB_CUDA(cudaMemsetAsync(c.x, 0, plane * (nz + 2) * 8, c.st));
+  KB_CUDA(cudaMemcpyAsync(c.x + plane, T, n * 8, cudaMemcpyHostToDevice, c.st));
+  KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
+  const int gf = (int)std::min<long>((rows + 255) / 256, (long)c.sms * 4);
+  k_flux<<<gf, 256, 0, c.st>>>(c.x + plane, c.code, C, D, c.qL, c.qR, c.partials);
+  KB_LAUNCHED();
+  k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gf, 4, c.S);
+  KB_LAUNCHED();
+  k_step_flux<<<1, 1, 0, c.st>>>(c.S);
+  KB_LAUNCHED();
+  Stencil s;
+  KB_TRY(stencil_setup(s, D, C, P.flags));
+  KB_TRY(stencil_launch<MODE_RESID>(s, 0, nullptr, nullptr));
+  k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 3, c.S);
+  KB_LAUNCHED();
+  KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
+  if (qL) KB_CUDA(cudaMemcpyAsync(qL, c.qL, rows * 8, cudaMemcpyDeviceToHost, c.st));
+  if (qR) KB_CUDA(cudaMemcpyAsync(qR, c.qR, rows * 8, cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  memset(out, 0, sizeof *out);
+  out->q_left = c.hS->ql;
+  out->q_right = c.hS->qr;
+  out->keff = (c.hS->ql + c.hS->qr) / 2 / (P.tr - P.tl);
+  out->energy_residual = c.hS->tmp[2];
+  out->rel_residual = sqrt(c.hS->tmp[1]);  // absolute 2-norm here: no ||b|| without an INIT pass
+  return 0;
+}
+
+int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, const keffb200_params* p, int reps,
+                             float* ms_per_apply) {
+  KB_TRY(need_ready());
+  if (!d_solid || !ms_per_apply || reps < 1) return fail(KEFFB200_EINVAL, "bad argument");
+  Ctx& c = ctx();
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz, 0, nz};
+  KB_TRY(stage_mask(d_solid, true, D));
+  const size_t plane = (size_t)nx * ny;
+  const Coef C = make_coef(nx, ny, nz, P);
+  k_make_code<<<c.sms * 8, 256, 0, c.st>>>(c.mask + plane, c.code, D, 0, 0);
+  KB_LAUNCHED();
+  KB_CUDA(cudaMemsetAsync(c.p, 0, plane * (nz + 2) * 8, c.st));
+  k_init_field<<<c.sms * 8, 256, 0, c.st>>>(c.p + plane, D, P.tl, P.tr, 0);
+  KB_LAUNCHED();
+  KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
+  Stencil s;
+  KB_TRY(stencil_setup(s, D, C, P.flags));
+  for (int i = 0; i < 3; i++) KB_TRY(stencil_launch<MODE_APPLY>(s, 1, c.q + plane, nullptr));
+  KB_CUDA(cudaEventRecord(c.ev0, c.st));
+  for (int i = 0; i < reps; i++) KB_TRY(stencil_launch<MODE_APPLY>(s, 1, c.q + plane, nullptr));
+  KB_CUDA(cudaEventRecord(c.ev1, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  float ms = 0;
+  KB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  *ms_per_apply = ms / reps;
+  return 0;
+}
+
+// ---- z-slab communicator -----------------------------------------------------------------------
+static int nccl_load() {
+  Nccl& n = ctx().nccl;
+  if (n.h) return 0;
+  n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!n.h) n.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!n.h) return fail(KEFFB200_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define KB_SYM(field, name)                                                  \
+  *(void**)(&n.field) = dlsym(n.h, name);                                    \
+  if (!n.field) return fail(KEFFB200_ENCCL, "libnccl lacks symbol %s", name)
+  KB_SYM(GetUniqueId, "ncclGetUniqueId");
+  KB_SYM(CommInitRank, "ncclCommInitRank");
+  KB_SYM(CommDestroy, "ncclCommDestroy");
+  KB_SYM(AllReduce, "ncclAllReduce");
+  KB_SYM(Send, "ncclSend");
+  KB_SYM(Recv, "ncclRecv");
+  KB_SYM(GroupStart, "ncclGroupStart");
+  KB_SYM(GroupEnd, "ncclGroupEnd");
+  KB_SYM(GetErrorString, "ncclGetErrorString");
+#undef KB_SYM
+  return 0;
+}
+
+int keffb200_comm_id(void* id128) {
+  KB_TRY(nccl_load());
+  return nccl_check(ctx().nccl.GetUniqueId(id128), "ncclGetUniqueId");
+}
+
+int keffb200_dist_init(int rank, int world, const void* id128) {
+  KB_TRY(need_ready());
+  Nccl& n = ctx().nccl;
+  if (world < 1 || rank < 0 || rank >= world) return fail(KEFFB200_EINVAL, "bad rank/world");
+  n.rank = rank;
+  n.world = world;
+  if (world == 1) return 0;
+  KB_TRY(nccl_load());
+  Id128 id;
+  memcpy(id.b, id128, 128);
+  KB_CUDA(cudaSetDevice(ctx().device));
+  return nccl_check(n.CommInitRank(&n.comm, world, id, rank), "ncclCommInitRank");
+}
+
+void keffb200_dist_shutdown(void) {
+  Nccl& n = ctx().nccl;
+  if (n.comm && n.CommDestroy) n.CommDestroy(n.comm);
+  n.comm = nullptr;
+  n.rank = 0;
+  n.world = 1;
+}
+
+}  // extern "C"
