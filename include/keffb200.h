@@ -129,6 +129,12 @@ int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_p
 int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, const keffb200_params* p,
                              int reps, float* ms_per_apply);
 
+/* Synthetic input generator for benchmarks and tests (no reference counterpart): voxel i of the
+ * range [first_index, first_index + n) is solid iff splitmix64(seed ^ i) < p * 2^64.  The same rule
+ * is implemented in Python (keff_cfd_b200/structures.py) so host and device agree bit for bit. */
+int keffb200_gen_bernoulli_dev(uint8_t* d_out, size_t n, unsigned long long first_index,
+                               unsigned long long seed, double p);
+
 #ifdef __cplusplus
 }
 #endif

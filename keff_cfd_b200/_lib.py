@@ -37,7 +37,7 @@ EXPORTS = [
     "keffb200_default_params", "keffb200_launch_count", "keffb200_solve2d", "keffb200_solve2d_batch",
     "keffb200_solve3d", "keffb200_solve3d_dev", "keffb200_solve2d_batch_dev", "keffb200_comm_id",
     "keffb200_dist_init", "keffb200_dist_shutdown", "keffb200_solve3d_slab_dev", "keffb200_apply",
-    "keffb200_flux", "keffb200_bench_apply_dev",
+    "keffb200_flux", "keffb200_bench_apply_dev", "keffb200_gen_bernoulli_dev",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def lib():
         L.keffb200_flux.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, dp, RP]
         L.keffb200_bench_apply_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, C.c_int,
                                                C.POINTER(C.c_float)]
+        L.keffb200_gen_bernoulli_dev.argtypes = [u8p, C.c_size_t, C.c_ulonglong, C.c_ulonglong, C.c_double]
         _lib = L
     return _lib
 

@@ -214,3 +214,13 @@ def bench_apply(solid_dev, params=None, reps=20, device=0):
     ms = C.c_float()
     check(lib().keffb200_bench_apply_dev(_addr(solid_dev), nx, ny, nz, C.byref(p), reps, C.byref(ms)))
     return ms.value
+
+
+def bernoulli_volume_dev(shape, p=0.5, seed=1234, z0=0, device=0):
+    """Device-side twin of structures.bernoulli_volume: CUDA u8 tensor [nz, ny, nx]."""
+    import torch
+    _lib.init(device)
+    nz, ny, nx = shape
+    out = torch.empty(shape, dtype=torch.uint8, device=f"cuda:{device}")
+    check(lib().keffb200_gen_bernoulli_dev(out.data_ptr(), nz * ny * nx, z0 * ny * nx, seed, p))
+    return out

@@ -646,6 +646,31 @@ int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, con
   return 0;
 }
 
+// ---- synthetic structures (bench / test utility) -----------------------------------------------
+__global__ void k_gen_bernoulli(uint8_t* out, size_t n, unsigned long long seed, unsigned long long thr,
+                                unsigned long long first) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long z = ((first + i) ^ seed) + 0x9E3779B97F4A7C15ull;  // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    out[i] = z < thr;
+  }
+}
+
+int keffb200_gen_bernoulli_dev(uint8_t* d_out, size_t n, unsigned long long first_index, unsigned long long seed,
+                               double p) {
+  KB_TRY(need_ready());
+  if (!d_out) return fail(KEFFB200_EINVAL, "null argument");
+  const double s = p * 18446744073709551616.0;
+  const unsigned long long thr = s >= 18446744073709551615.0 ? ~0ull : (unsigned long long)s;
+  k_gen_bernoulli<<<ctx().sms * 8, 256, 0, ctx().st>>>(d_out, n, seed, thr, first_index);
+  KB_LAUNCHED();
+  KB_CUDA(cudaGetLastError());
+  KB_CUDA(cudaStreamSynchronize(ctx().st));
+  return 0;
+}
+
 // ---- z-slab communicator -----------------------------------------------------------------------
 static int nccl_load() {
   Nccl& n = ctx().nccl;

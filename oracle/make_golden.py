@@ -104,6 +104,41 @@ def binary2d():
     shutil.rmtree(d)
 
 
+def discrete():
+    """Discrete solutions (oracle PCG on the reference's own assembled system, eps 1e-12) of every
+    fixture structure: the limit the tightened reference converges to (checked by
+    tests/test_oracle.py against the ref2d_*/ref3d_* records above)."""
+    from keff_cfd_b200 import structures as S
+    from keff_cfd_b200.api import structure_from_image
+    out = {}
+    for tag in ("00009", "00000"):
+        img = np.load(os.path.join(GOLD, f"img_{tag}.npy"))
+        for amp in (1, 2):
+            g = S.to_gray(structure_from_image(img, amp, amp))
+            d = refbind.orc_discrete(g)
+            out[f"img_{tag}_amp{amp}"] = {k: d[k] for k in ("keff", "Q1", "Q2", "iters", "relres")}
+            if amp == 1:
+                np.save(os.path.join(GOLD, f"discrete_img_{tag}_T.npy"), d["T"])
+    for name in ("schwarz163", "schwarz091"):
+        m = np.unpackbits(np.load(os.path.join(GOLD, name + "_bits.npy"))).reshape(128, 128, 128)
+        d = refbind.orc_discrete(m)
+        out[name] = {k: d[k] for k in ("keff", "Q1", "Q2", "iters", "relres")}
+        np.save(os.path.join(GOLD, f"discrete_{name}_Tsub4.npy"), d["T"][::4, ::4, ::4].copy())
+        # x<->y and x<->z transposes must give the same Keff (the TPMS structures are symmetric)
+        out[name]["keff_transposed_xy"] = refbind.orc_discrete(np.ascontiguousarray(m.transpose(0, 2, 1)))["keff"]
+    for n in (32, 64):
+        m = S.bernoulli_volume((n, n, n), 0.5, 1234)
+        d = refbind.orc_discrete(m)
+        out[f"bernoulli_{n}_seed1234"] = {k: d[k] for k in ("keff", "Q1", "Q2", "iters", "relres")}
+    for i in range(4):
+        d = refbind.orc_discrete(S.to_gray(S.disc_image(i)))
+        out[f"disc_image_{i}"] = {k: d[k] for k in ("keff", "Q1", "Q2", "iters", "relres")}
+    json.dump(out, open(os.path.join(GOLD, "discrete.json"), "w"), indent=1, sort_keys=True)
+    for k, v in out.items():
+        print(k, v)
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
-    {"prep": prep, "ref2d": ref2d, "binary2d": binary2d}.get(cmd, lambda: ref3d(*sys.argv[2:4]))()
+    {"prep": prep, "ref2d": ref2d, "binary2d": binary2d, "discrete": discrete}.get(
+        cmd, lambda: ref3d(*sys.argv[2:4]))()
