@@ -170,16 +170,27 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
       }
     }
     const int coff = (ly + 1) * BOXW + lx + 2;  // my cell pair inside a staged plane
-    double2 pm, pc, pp;
+    long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of my first cell in plane zb
+    unsigned cnext = active ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
+    double2 pc, pp;
+    // Flux form: q_P = sum_faces c_f (p_P - p_f) + c_wall p_P.  Every face conductance and every
+    // face flux is evaluated once: the flux through the x face shared by my two cells feeds both,
+    // and the flux through the z face towards the next plane is carried to the next step (gz).
+    double gza = 0.0, gzb = 0.0;
     {
       const uint32_t s0 = seq % NST, s1 = (seq + 1) % NST;
       mbar_wait(&full[s0], (seq / NST) & 1);
-      pm = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s0 * STAGE_STRIDE) + coff);
+      const double2 pm =
+          *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s0 * STAGE_STRIDE) + coff);
       mbar_wait(&full[s1], ((seq + 1) / NST) & 1);
       pc = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s1 * STAGE_STRIDE) + coff);
+      if (D.z0 + zb != 0) {  // face between plane zb-1 and zb, seen from plane zb-1's side
+        const unsigned ca = cnext & 0xffu, cb = cnext >> 8;
+        const double sa = (ca & C_PH) ? C.same[2][1] : C.same[2][0], sb = (cb & C_PH) ? C.same[2][1] : C.same[2][0];
+        gza = ((ca & C_F) ? C.diff[2] : sa) * (pm.x - pc.x);
+        gzb = ((cb & C_F) ? C.diff[2] : sb) * (pm.y - pc.y);
+      }
     }
-    long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of my first cell in plane zb
-    unsigned cnext = active ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
 
     for (int k = 1; k <= len; k++) {
       const int lz = zb + k - 1;
@@ -199,21 +210,53 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
         const double2 pn = *reinterpret_cast<const double2*>(cur + coff - BOXW);
         const double2 ps = *reinterpret_cast<const double2*>(cur + coff + BOXW);
         const double pw = cur[coff - 1], pe = cur[coff + 2];
-        const bool z0 = D.z0 + lz == 0, z1 = D.z0 + lz == D.nzg - 1;
+        const bool z1 = D.z0 + lz == D.nzg - 1;
         const unsigned ca = cc & 0xffu, cb = cc >> 8;
-        const Faces Fa = faces_of(C, ca, ax0, false, y0, y1, z0, z1);
-        const Faces Fb = faces_of(C, cb, false, bx1, y0, y1, z0, z1);
-        const double qa = Fa.diag * pc.x - Fa.w * pw - Fa.e * pc.y - Fa.n * pn.x - Fa.s * ps.x - Fa.f * pm.x -
-                          Fa.b * pp.x;
-        const double qb = Fb.diag * pc.y - Fb.w * pc.x - Fb.e * pe - Fb.n * pn.y - Fb.s * ps.y - Fb.f * pm.y -
-                          Fb.b * pp.y;
+        const bool pha = ca & C_PH, phb = cb & C_PH;
+        const double sxa = pha ? C.same[0][1] : C.same[0][0], sxb = phb ? C.same[0][1] : C.same[0][0];
+        const double sya = pha ? C.same[1][1] : C.same[1][0], syb = phb ? C.same[1][1] : C.same[1][0];
+        const double sza = pha ? C.same[2][1] : C.same[2][0], szb = phb ? C.same[2][1] : C.same[2][0];
+        // incoming z flux (from the plane below), then the x face shared by my two cells
+        double qa = -gza, qb = -gzb;
+        const double gs = ((ca & C_E) ? C.diff[0] : sxa) * (pc.x - pc.y);
+        qa += gs;
+        qb -= gs;
+        if (!ax0) qa += ((ca & C_W) ? C.diff[0] : sxa) * (pc.x - pw);
+        else qa += (pha ? C.wall[1] : C.wall[0]) * pc.x;
+        if (!bx1) qb += ((cb & C_E) ? C.diff[0] : sxb) * (pc.y - pe);
+        else qb += (phb ? C.wall[1] : C.wall[0]) * pc.y;
+        if (!y0) {
+          qa += ((ca & C_N) ? C.diff[1] : sya) * (pc.x - pn.x);
+          qb += ((cb & C_N) ? C.diff[1] : syb) * (pc.y - pn.y);
+        }
+        if (!y1) {
+          qa += ((ca & C_S) ? C.diff[1] : sya) * (pc.x - ps.x);
+          qb += ((cb & C_S) ? C.diff[1] : syb) * (pc.y - ps.y);
+        }
+        if (!z1) {
+          gza = ((ca & C_B) ? C.diff[2] : sza) * (pc.x - pp.x);
+          gzb = ((cb & C_B) ? C.diff[2] : szb) * (pc.y - pp.y);
+          qa += gza;
+          qb += gzb;
+        }
         double2 u, v;
-        cell_epilogue<MODE>(C, ca, ax0, false, Fa, pc.x, qa, u.x, v.x, acc);
-        cell_epilogue<MODE>(C, cb, false, bx1, Fb, pc.y, qb, u.y, v.y, acc);
+        if (MODE == MODE_APPLY) {
+          u.x = qa;
+          u.y = qb;
+          acc[0] += pc.x * qa + pc.y * qb;
+        } else {
+          Faces Fa, Fb;
+          if (MODE == MODE_INIT) {
+            const bool z0 = D.z0 + lz == 0;
+            Fa.diag = diag_of(C, ca, ax0, false, y0, y1, z0, z1);
+            Fb.diag = diag_of(C, cb, false, bx1, y0, y1, z0, z1);
+          }
+          cell_epilogue<MODE>(C, ca, ax0, false, Fa, pc.x, qa, u.x, v.x, acc);
+          cell_epilogue<MODE>(C, cb, false, bx1, Fb, pc.y, qb, u.y, v.y, acc);
+        }
         if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci) = u;
         if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci) = v;
       }
-      pm = pc;
       pc = pp;
       ci += plane;
     }
@@ -232,6 +275,27 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
 //   k_cg_update : alpha = r.z / p.q;  x += alpha p;  r -= alpha q;  partials {r.(r/a_P), r.r}
 //   k_cg_dir    : beta = r.z_new / r.z_old;  p = r/a_P + beta p
 // ------------------------------------------------------------------------------------------------
+template <int V>
+struct VecD;
+template <>
+struct VecD<1> {
+  double v[1];
+  __device__ __forceinline__ void load(const double* p) { v[0] = *p; }
+  __device__ __forceinline__ void store(double* p) const { *p = v[0]; }
+};
+template <>
+struct VecD<2> {
+  double v[2];
+  __device__ __forceinline__ void load(const double* p) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x;
+    v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+};
+
+// V cells per thread per step (V = 2 needs nx even: 16-byte aligned pairs)
+template <int V>
 __global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, double* __restrict__ r,
                                                    const double* __restrict__ p, const double* __restrict__ q,
                                                    const uint8_t* __restrict__ code, const Coef C, const Dom D,
@@ -246,15 +310,25 @@ __global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, doubl
     const int y = (int)(row % D.ny), z = (int)(row / D.ny);
     const bool y0 = y == 0, y1 = y == D.ny - 1, z0 = D.z0 + z == 0, z1 = D.z0 + z == D.nzg - 1;
     const long base = row * D.nx;
-    for (int xx = threadIdx.x; xx < D.nx; xx += blockDim.x) {
+    for (int xx = threadIdx.x * V; xx < D.nx; xx += blockDim.x * V) {
       const long i = base + xx;
-      const double d = diag_of(C, code[i], xx == 0, xx == D.nx - 1, y0, y1, z0, z1);
-      const double pi = p[i], qi = q[i];
-      x[i] += alpha * pi;
-      const double ri = r[i] - alpha * qi;
-      r[i] = ri;
-      acc[0] += ri * (ri / d);
-      acc[1] += ri * ri;
+      VecD<V> vx, vr, vp, vq;
+      vx.load(x + i);
+      vr.load(r + i);
+      vp.load(p + i);
+      vq.load(q + i);
+      unsigned cc = V == 2 ? *reinterpret_cast<const unsigned short*>(code + i) : code[i];
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        const double d = diag_of(C, (cc >> (8 * j)) & 0xffu, xx + j == 0, xx + j == D.nx - 1, y0, y1, z0, z1);
+        vx.v[j] += alpha * vp.v[j];
+        const double ri = vr.v[j] - alpha * vq.v[j];
+        vr.v[j] = ri;
+        acc[0] += ri * (ri / d);
+        acc[1] += ri * ri;
+      }
+      vx.store(x + i);
+      vr.store(r + i);
     }
   }
   block_sum<2>(acc, red);
@@ -264,6 +338,7 @@ __global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, doubl
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(256) k_cg_dir(double* __restrict__ p, const double* __restrict__ r,
                                                 const uint8_t* __restrict__ code, const Coef C, const Dom D,
                                                 const Scal* __restrict__ S, int par) {
@@ -274,10 +349,18 @@ __global__ void __launch_bounds__(256) k_cg_dir(double* __restrict__ p, const do
     const int y = (int)(row % D.ny), z = (int)(row / D.ny);
     const bool y0 = y == 0, y1 = y == D.ny - 1, z0 = D.z0 + z == 0, z1 = D.z0 + z == D.nzg - 1;
     const long base = row * D.nx;
-    for (int xx = threadIdx.x; xx < D.nx; xx += blockDim.x) {
+    for (int xx = threadIdx.x * V; xx < D.nx; xx += blockDim.x * V) {
       const long i = base + xx;
-      const double d = diag_of(C, code[i], xx == 0, xx == D.nx - 1, y0, y1, z0, z1);
-      p[i] = r[i] / d + beta * p[i];
+      VecD<V> vr, vp;
+      vr.load(r + i);
+      vp.load(p + i);
+      unsigned cc = V == 2 ? *reinterpret_cast<const unsigned short*>(code + i) : code[i];
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        const double d = diag_of(C, (cc >> (8 * j)) & 0xffu, xx + j == 0, xx + j == D.nx - 1, y0, y1, z0, z1);
+        vp.v[j] = vr.v[j] / d + beta * vp.v[j];
+      }
+      vp.store(p + i);
     }
   }
 }

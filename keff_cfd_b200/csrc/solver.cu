@@ -199,7 +199,10 @@ static int stencil_launch(const Stencil& s, int which, double* o0, double* o1) {
   return 0;
 }
 
-static int vec_threads(int nx) { return std::min(256, std::max(32, (nx + 31) / 32 * 32)); }
+static int vec_threads(int nx, int V) {
+  const int lanes = (nx + V - 1) / V;
+  return std::min(256, std::max(32, (lanes + 31) / 32 * 32));
+}
 
 // ---- the solve ----------------------------------------------------------------------------------
 // d_mask_halo: (nz+2) planes (plane 0 and nz+1 are the slab neighbours' planes or don't-care);
@@ -216,7 +219,8 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   const Coef C = make_coef(D.nx, D.ny, D.nzg, P);
   const bool lo = nc.world > 1 && D.z0 > 0, hi = nc.world > 1 && D.z0 + D.nz < D.nzg;
   double *x = c.x + plane, *r = c.r + plane, *p = c.p + plane, *q = c.q + plane;
-  const int vt = vec_threads(D.nx);
+  const int V = D.nx % 2 == 0 ? 2 : 1;
+  const int vt = vec_threads(D.nx, V);
   const long rows = (long)D.ny * D.nz;
   const int gv = (int)std::min<long>(rows, (long)c.sms * (2048 / vt));
   const int gf = (int)std::min<long>((rows + 255) / 256, (long)c.sms * 4);
@@ -270,14 +274,16 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 0, c.S);
       KB_LAUNCHED();
       KB_TRY(allreduce_tmp(&c.S->pq, 1));
-      k_cg_update<<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
+      if (V == 2) k_cg_update<2><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
+      else k_cg_update<1><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
       KB_LAUNCHED();
       k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gv, 1, c.S);
       KB_LAUNCHED();
       KB_TRY(allreduce_tmp(c.S->tmp, 2));
       k_step_iter<<<1, 1, 0, c.st>>>(c.S, par);
       KB_LAUNCHED();
-      k_cg_dir<<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
+      if (V == 2) k_cg_dir<2><<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
+      else k_cg_dir<1><<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
       KB_LAUNCHED();
     }
     // host-visible check: flux, Keff, flags
