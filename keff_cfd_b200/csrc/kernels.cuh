@@ -117,20 +117,29 @@ __global__ void __launch_bounds__(256) k_stencil_plain(const double* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA stencil kernel (nx even).  Work item = (64 x 8) xy tile x one z chunk.  A CTA marches its item
-// in z: planes (with a 2-cell x halo and 1-row y halo, zero-filled outside the domain by the TMA
-// unit) stream into an NST-deep shared-memory ring via cp.async.bulk.tensor + mbarrier; each thread
-// owns two x-adjacent cells and keeps their z-1 / z / z+1 values in registers, so every field value
-// is fetched from L2/HBM once per tile and read from shared memory ~3.5 times.
+// TMA stencil kernel (nx even).  Work item = (64 x 16) xy tile x one z chunk.  A CTA marches its item
+// in z: planes (2-cell x halo, 1-row y halo, zero-filled outside the domain by the TMA unit) stream
+// into an NST-deep shared-memory ring via cp.async.bulk.tensor + mbarrier.  Each thread owns a 2x2
+// block of cells and keeps the current and next plane's values in registers, so a field value is
+// fetched from L2/HBM once per tile and read from shared memory 3 times.
+//
+// Flux form: q_P = sum_faces c_f (p_P - p_f).  Each face conductance and flux is evaluated once: the
+// four faces inside my 2x2 block feed both of their cells, and the flux towards the next plane is
+// carried to the next step.  Domain boundaries cost nothing in the loop: the fixed-temperature wall
+// is a face of conductance c_wall whose neighbour value is the TMA's zero fill, an adiabatic face is
+// a face of conductance 0 -- both folded into per-thread "same phase" constants of the four outward
+// faces (the code bits of boundary faces are 0 by construction).
 // Items are dealt round-robin to a fixed grid (deterministic partial sums).
 // ------------------------------------------------------------------------------------------------
-constexpr int TX = 64, TY = 8, BOXW = TX + 4, BOXH = TY + 2, NST = 4, NTHR = 256;
+constexpr int TX = 64, TY = 16, BOXW = TX + 4, BOXH = TY + 2, NST = 4, NTHR = 256;
 constexpr int STAGE_BYTES = BOXW * BOXH * 8;
 constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
 
 struct Plan {
   int ntx, nty, nzc, zlen, nitems;
 };
+
+__device__ __forceinline__ double pick(bool c, double a, double b) { return c ? a : b; }
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CUtensorMap tm,
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
   __shared__ __align__(8) uint64_t full[NST];
   __shared__ double red[32 * 3];
   if (S->done) return;
-  const int tid = threadIdx.x, lx = (tid & 31) * 2, ly = tid >> 5;
+  const int tid = threadIdx.x, lx = (tid & 31) * 2, ly = (tid >> 5) * 2;
   if (tid == 0) {
     for (int s = 0; s < NST; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -149,15 +158,26 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
   uint32_t seq = 0;  // planes streamed so far by this CTA (identical in every thread)
   double acc[3] = {0, 0, 0};
   const long plane = (long)D.nx * D.ny;
+  const int coff = (ly + 1) * BOXW + lx + 2;  // cell a of my 2x2 block inside a staged plane
+  // interior "same phase" conductances [phase]
+  const double sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0], sy1 = C.same[1][1];
+  const double sz0 = C.same[2][0], sz1 = C.same[2][1];
+  const double dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
 
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
     const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
     const int len = min(D.nz, zb + P.zlen) - zb, nplanes = len + 2;
     const int gx = xo + lx, gy = yo + ly;
-    const bool active = gx < D.nx && gy < D.ny;
-    const bool y0 = gy == 0, y1 = gy == D.ny - 1;
-    const bool ax0 = gx == 0, bx1 = gx + 1 == D.nx - 1;
+    const bool colv = gx < D.nx;                       // nx even: both columns valid or none
+    const bool row0 = colv && gy < D.ny, row1 = colv && gy + 1 < D.ny;
+    // outward faces of my block: W (cells a,c), E (b,d), N (a,b), S (c,d); inner y face (a|c, b|d)
+    const bool ax0 = gx == 0, bx1 = gx + 1 == D.nx - 1, yt = gy == 0, yb = gy + 1 == D.ny - 1;
+    const double w0 = ax0 ? C.wall[0] : sx0, w1 = ax0 ? C.wall[1] : sx1;
+    const double e0 = bx1 ? C.wall[0] : sx0, e1 = bx1 ? C.wall[1] : sx1;
+    const double n0 = yt ? 0.0 : sy0, n1 = yt ? 0.0 : sy1;
+    const double s0 = (yb || !row1) ? 0.0 : sy0, s1 = (yb || !row1) ? 0.0 : sy1;
+    const double m0 = row1 ? sy0 : 0.0, m1 = row1 ? sy1 : 0.0;
 
     __syncthreads();  // ring is idle (previous item fully consumed; barriers initialised)
     if (tid == 0) {
@@ -169,26 +189,26 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
         tma_load_3d(tiles + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + k);
       }
     }
-    const int coff = (ly + 1) * BOXW + lx + 2;  // my cell pair inside a staged plane
-    long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of my first cell in plane zb
-    unsigned cnext = active ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
-    double2 pc, pp;
-    // Flux form: q_P = sum_faces c_f (p_P - p_f) + c_wall p_P.  Every face conductance and every
-    // face flux is evaluated once: the flux through the x face shared by my two cells feeds both,
-    // and the flux through the z face towards the next plane is carried to the next step (gz).
-    double gza = 0.0, gzb = 0.0;
+    long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of cell a in plane zb
+    unsigned cn0 = row0 ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
+    unsigned cn1 = row1 ? *reinterpret_cast<const unsigned short*>(code + ci + D.nx) : 0u;
+    double2 pt, pb, nt, nb;               // current / next plane, top row (a,b) and bottom row (c,d)
+    double ga = 0.0, gb = 0.0, gc = 0.0, gd = 0.0;  // flux into my cells from the plane below
     {
-      const uint32_t s0 = seq % NST, s1 = (seq + 1) % NST;
-      mbar_wait(&full[s0], (seq / NST) & 1);
-      const double2 pm =
-          *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s0 * STAGE_STRIDE) + coff);
-      mbar_wait(&full[s1], ((seq + 1) / NST) & 1);
-      pc = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + s1 * STAGE_STRIDE) + coff);
-      if (D.z0 + zb != 0) {  // face between plane zb-1 and zb, seen from plane zb-1's side
-        const unsigned ca = cnext & 0xffu, cb = cnext >> 8;
-        const double sa = (ca & C_PH) ? C.same[2][1] : C.same[2][0], sb = (cb & C_PH) ? C.same[2][1] : C.same[2][0];
-        gza = ((ca & C_F) ? C.diff[2] : sa) * (pm.x - pc.x);
-        gzb = ((cb & C_F) ? C.diff[2] : sb) * (pm.y - pc.y);
+      const uint32_t q0 = seq % NST, q1 = (seq + 1) % NST;
+      mbar_wait(&full[q0], (seq / NST) & 1);
+      const double* lo = reinterpret_cast<const double*>(tiles + q0 * STAGE_STRIDE) + coff;
+      const double2 mt = *reinterpret_cast<const double2*>(lo), mb = *reinterpret_cast<const double2*>(lo + BOXW);
+      mbar_wait(&full[q1], ((seq + 1) / NST) & 1);
+      const double* c0 = reinterpret_cast<const double*>(tiles + q1 * STAGE_STRIDE) + coff;
+      pt = *reinterpret_cast<const double2*>(c0);
+      pb = *reinterpret_cast<const double2*>(c0 + BOXW);
+      if (D.z0 + zb != 0) {  // face between plane zb-1 and zb
+        const unsigned ca = cn0 & 0xffu, cb = cn0 >> 8, cc = cn1 & 0xffu, cd = cn1 >> 8;
+        ga = pick(ca & C_F, dfz, pick(ca & C_PH, sz1, sz0)) * (mt.x - pt.x);
+        gb = pick(cb & C_F, dfz, pick(cb & C_PH, sz1, sz0)) * (mt.y - pt.y);
+        gc = pick(cc & C_F, dfz, pick(cc & C_PH, sz1, sz0)) * (mb.x - pb.x);
+        gd = pick(cd & C_F, dfz, pick(cd & C_PH, sz1, sz0)) * (mb.y - pb.y);
       }
     }
 
@@ -202,62 +222,92 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
       }
       const uint32_t sc = (seq + k) % NST, sn = (seq + k + 1) % NST;
       mbar_wait(&full[sn], ((seq + k + 1) / NST) & 1);
-      const double* cur = reinterpret_cast<const double*>(tiles + sc * STAGE_STRIDE);
-      pp = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tiles + sn * STAGE_STRIDE) + coff);
-      const unsigned cc = cnext;
-      if (active && k < len) cnext = *reinterpret_cast<const unsigned short*>(code + ci + plane);
-      if (active) {
-        const double2 pn = *reinterpret_cast<const double2*>(cur + coff - BOXW);
-        const double2 ps = *reinterpret_cast<const double2*>(cur + coff + BOXW);
-        const double pw = cur[coff - 1], pe = cur[coff + 2];
-        const bool z1 = D.z0 + lz == D.nzg - 1;
-        const unsigned ca = cc & 0xffu, cb = cc >> 8;
-        const bool pha = ca & C_PH, phb = cb & C_PH;
-        const double sxa = pha ? C.same[0][1] : C.same[0][0], sxb = phb ? C.same[0][1] : C.same[0][0];
-        const double sya = pha ? C.same[1][1] : C.same[1][0], syb = phb ? C.same[1][1] : C.same[1][0];
-        const double sza = pha ? C.same[2][1] : C.same[2][0], szb = phb ? C.same[2][1] : C.same[2][0];
-        // incoming z flux (from the plane below), then the x face shared by my two cells
-        double qa = -gza, qb = -gzb;
-        const double gs = ((ca & C_E) ? C.diff[0] : sxa) * (pc.x - pc.y);
-        qa += gs;
-        qb -= gs;
-        if (!ax0) qa += ((ca & C_W) ? C.diff[0] : sxa) * (pc.x - pw);
-        else qa += (pha ? C.wall[1] : C.wall[0]) * pc.x;
-        if (!bx1) qb += ((cb & C_E) ? C.diff[0] : sxb) * (pc.y - pe);
-        else qb += (phb ? C.wall[1] : C.wall[0]) * pc.y;
-        if (!y0) {
-          qa += ((ca & C_N) ? C.diff[1] : sya) * (pc.x - pn.x);
-          qb += ((cb & C_N) ? C.diff[1] : syb) * (pc.y - pn.y);
-        }
-        if (!y1) {
-          qa += ((ca & C_S) ? C.diff[1] : sya) * (pc.x - ps.x);
-          qb += ((cb & C_S) ? C.diff[1] : syb) * (pc.y - ps.y);
-        }
-        if (!z1) {
-          gza = ((ca & C_B) ? C.diff[2] : sza) * (pc.x - pp.x);
-          gzb = ((cb & C_B) ? C.diff[2] : szb) * (pc.y - pp.y);
-          qa += gza;
-          qb += gzb;
-        }
-        double2 u, v;
-        if (MODE == MODE_APPLY) {
-          u.x = qa;
-          u.y = qb;
-          acc[0] += pc.x * qa + pc.y * qb;
-        } else {
-          Faces Fa, Fb;
-          if (MODE == MODE_INIT) {
-            const bool z0 = D.z0 + lz == 0;
-            Fa.diag = diag_of(C, ca, ax0, false, y0, y1, z0, z1);
-            Fb.diag = diag_of(C, cb, false, bx1, y0, y1, z0, z1);
-          }
-          cell_epilogue<MODE>(C, ca, ax0, false, Fa, pc.x, qa, u.x, v.x, acc);
-          cell_epilogue<MODE>(C, cb, false, bx1, Fb, pc.y, qb, u.y, v.y, acc);
-        }
-        if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci) = u;
-        if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci) = v;
+      const double* cur = reinterpret_cast<const double*>(tiles + sc * STAGE_STRIDE) + coff;
+      const double* nxt = reinterpret_cast<const double*>(tiles + sn * STAGE_STRIDE) + coff;
+      nt = *reinterpret_cast<const double2*>(nxt);
+      nb = *reinterpret_cast<const double2*>(nxt + BOXW);
+      const unsigned k0 = cn0, k1 = cn1;
+      if (k < len) {
+        if (row0) cn0 = *reinterpret_cast<const unsigned short*>(code + ci + plane);
+        if (row1) cn1 = *reinterpret_cast<const unsigned short*>(code + ci + plane + D.nx);
       }
-      pc = pp;
+      const double2 pn = *reinterpret_cast<const double2*>(cur - BOXW);
+      const double2 ps = *reinterpret_cast<const double2*>(cur + 2 * BOXW);
+      const double pwt = cur[-1], pet = cur[2], pwb = cur[BOXW - 1], peb = cur[BOXW + 2];
+      const unsigned ca = k0 & 0xffu, cb = k0 >> 8, cc = k1 & 0xffu, cd = k1 >> 8;
+      const bool fa = ca & C_PH, fb = cb & C_PH, fc = cc & C_PH, fd = cd & C_PH;
+      // start from the flux that entered from the plane below
+      double qa = -ga, qb = -gb, qc = -gc, qd = -gd;
+      double g;
+      // x faces: W wall/neighbour, inner, E  (top row, bottom row)
+      qa += pick(ca & C_W, dfx, pick(fa, w1, w0)) * (pt.x - pwt);
+      g = pick(ca & C_E, dfx, pick(fa, sx1, sx0)) * (pt.x - pt.y);
+      qa += g;
+      qb -= g;
+      qb += pick(cb & C_E, dfx, pick(fb, e1, e0)) * (pt.y - pet);
+      qc += pick(cc & C_W, dfx, pick(fc, w1, w0)) * (pb.x - pwb);
+      g = pick(cc & C_E, dfx, pick(fc, sx1, sx0)) * (pb.x - pb.y);
+      qc += g;
+      qd -= g;
+      qd += pick(cd & C_E, dfx, pick(fd, e1, e0)) * (pb.y - peb);
+      // y faces: N, inner, S  (left column, right column)
+      qa += pick(ca & C_N, dfy, pick(fa, n1, n0)) * (pt.x - pn.x);
+      g = pick(ca & C_S, dfy, pick(fa, m1, m0)) * (pt.x - pb.x);
+      qa += g;
+      qc -= g;
+      qc += pick(cc & C_S, dfy, pick(fc, s1, s0)) * (pb.x - ps.x);
+      qb += pick(cb & C_N, dfy, pick(fb, n1, n0)) * (pt.y - pn.y);
+      g = pick(cb & C_S, dfy, pick(fb, m1, m0)) * (pt.y - pb.y);
+      qb += g;
+      qd -= g;
+      qd += pick(cd & C_S, dfy, pick(fd, s1, s0)) * (pb.y - ps.y);
+      // z faces towards the next plane (absent at the global top)
+      if (D.z0 + lz != D.nzg - 1) {
+        ga = pick(ca & C_B, dfz, pick(fa, sz1, sz0)) * (pt.x - nt.x);
+        gb = pick(cb & C_B, dfz, pick(fb, sz1, sz0)) * (pt.y - nt.y);
+        gc = pick(cc & C_B, dfz, pick(fc, sz1, sz0)) * (pb.x - nb.x);
+        gd = pick(cd & C_B, dfz, pick(fd, sz1, sz0)) * (pb.y - nb.y);
+        qa += ga;
+        qb += gb;
+        qc += gc;
+        qd += gd;
+      }
+      if (MODE == MODE_APPLY) {
+        if (row0) {
+          *reinterpret_cast<double2*>(o0 + ci) = make_double2(qa, qb);
+          acc[0] += pt.x * qa + pt.y * qb;
+        }
+        if (row1) {
+          *reinterpret_cast<double2*>(o0 + ci + D.nx) = make_double2(qc, qd);
+          acc[0] += pb.x * qc + pb.y * qd;
+        }
+      } else {
+        const bool z0 = D.z0 + lz == 0, z1 = D.z0 + lz == D.nzg - 1;
+        Faces Fa, Fb;
+        double2 u, v;
+        if (row0) {
+          if (MODE == MODE_INIT) {
+            Fa.diag = diag_of(C, ca, ax0, false, yt, gy == D.ny - 1, z0, z1);
+            Fb.diag = diag_of(C, cb, false, bx1, yt, gy == D.ny - 1, z0, z1);
+          }
+          cell_epilogue<MODE>(C, ca, ax0, false, Fa, pt.x, qa, u.x, v.x, acc);
+          cell_epilogue<MODE>(C, cb, false, bx1, Fb, pt.y, qb, u.y, v.y, acc);
+          if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci) = u;
+          if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci) = v;
+        }
+        if (row1) {
+          if (MODE == MODE_INIT) {
+            Fa.diag = diag_of(C, cc, ax0, false, false, yb, z0, z1);
+            Fb.diag = diag_of(C, cd, false, bx1, false, yb, z0, z1);
+          }
+          cell_epilogue<MODE>(C, cc, ax0, false, Fa, pb.x, qc, u.x, v.x, acc);
+          cell_epilogue<MODE>(C, cd, false, bx1, Fb, pb.y, qd, u.y, v.y, acc);
+          if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci + D.nx) = u;
+          if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci + D.nx) = v;
+        }
+      }
+      pt = nt;
+      pb = nb;
       ci += plane;
     }
     seq += nplanes;
