@@ -59,6 +59,7 @@ struct Ctx {
   size_t cap_batch = 0;
   void* batch_ws = nullptr;
   Nccl nccl;
+  bool dist_active = false;  // true only inside a slab solve: halo exchange + all-reduces enabled
 };
 
 inline Ctx& ctx() {

@@ -85,14 +85,14 @@ static int nccl_check(int rc, const char* what) {
 
 static int allreduce_tmp(double* dptr, int count) {
   Nccl& n = ctx().nccl;
-  if (n.world <= 1 || !n.comm) return 0;
+  if (n.world <= 1 || !n.comm || !ctx().dist_active) return 0;
   return nccl_check(n.AllReduce(dptr, dptr, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, n.comm, ctx().st), "ncclAllReduce");
 }
 
 // exchange the boundary planes of a halo'ed field with the z neighbours (f points at the halo plane)
 static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
   Nccl& n = ctx().nccl;
-  if (n.world <= 1 || !n.comm) return 0;
+  if (n.world <= 1 || !n.comm || !ctx().dist_active) return 0;
   const size_t plane = (size_t)D.nx * D.ny;
   double* lo_halo = f_halo;
   double* first = f_halo + plane;
@@ -217,7 +217,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   KB_TRY(ensure_ws(D));
   const size_t plane = (size_t)D.nx * D.ny, n = plane * D.nz;
   const Coef C = make_coef(D.nx, D.ny, D.nzg, P);
-  const bool lo = nc.world > 1 && D.z0 > 0, hi = nc.world > 1 && D.z0 + D.nz < D.nzg;
+  const bool lo = c.dist_active && D.z0 > 0, hi = c.dist_active && D.z0 + D.nz < D.nzg;
   double *x = c.x + plane, *r = c.r + plane, *p = c.p + plane, *q = c.q + plane;
   const int V = D.nx % 2 == 0 ? 2 : 1;
   const int vt = vec_threads(D.nx, V);
@@ -513,7 +513,10 @@ int keffb200_solve3d_slab_dev(const uint8_t* d_solid_halo, int nx, int ny, int n
   const keffb200_params P = norm_params(p);
   Dom D{nx, ny, nz_local, z0, nz_global};
   KB_TRY(ensure_ws(D));
-  return solve_grid(d_solid_halo, D, P, nullptr, d_T_out, nullptr, nullptr, out);
+  ctx().dist_active = ctx().nccl.world > 1;
+  const int rc = solve_grid(d_solid_halo, D, P, nullptr, d_T_out, nullptr, nullptr, out);
+  ctx().dist_active = false;
+  return rc;
 }
 
 int keffb200_solve2d_batch_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params* p,
