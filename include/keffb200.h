@@ -47,6 +47,8 @@ typedef struct keffb200_params {
 } keffb200_params;
 
 #define KEFFB200_F_NO_TMA 1      /* use the plain global-load stencil kernel (debug / odd nx) */
+#define KEFFB200_F_BATCH_GLOBAL 4 /* 2D batches: force the global-memory FP64 kernel (the on-chip
+                                    mixed-precision kernel is used when nx<=128, nx%4==0, ny<=128, ny%8==0) */
 #define KEFFB200_F_ZERO_INIT 2   /* start from T = tl everywhere (the reference's actual T0,
                                     Keff2D/keff2D.h:584-611) instead of the linear ramp */
 

@@ -8,29 +8,11 @@
 // CTAs pull images from an atomic counter, so the grid stays full whatever the per-image iteration
 // counts are, and per-image results do not depend on the schedule.
 #include "context.cuh"
-#include "common.cuh"
+#include "batch2d_onchip.cuh"
 
 namespace kb {
 
 Coef make_coef(int nx, int ny, int nzg, const keffb200_params& P);
-
-struct BatchOut {
-  double ql, qr, rr, bb, r1;
-  long long it;
-  int status, pad;
-};
-
-template <int N>
-__device__ __forceinline__ void block_allsum(double (&v)[N], double* red, double* bc) {
-  block_sum<N>(v, red);
-  if (threadIdx.x == 0)
-#pragma unroll
-    for (int j = 0; j < N; j++) bc[j] = v[j];
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < N; j++) v[j] = bc[j];
-  __syncthreads();
-}
 
 // v1: CG vectors live in a per-CTA slice of global memory that stays L2-resident
 // (148 CTAs x 4 vectors x 128 KiB = 74 MiB < 126 MB L2 for 128x128 images).
@@ -232,11 +214,32 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
   int* counter = (int*)(res + n_img);
   uint8_t* codes = (uint8_t*)(counter + 16);
   const Coef C = make_coef(nx, ny, 1, P);
+  const bool onchip = !(P.flags & KEFFB200_F_BATCH_GLOBAL) && nx <= 128 && nx % 4 == 0 && ny <= 128 && ny % 8 == 0;
   KB_CUDA(cudaEventRecord(c.ev0, c.st));
   KB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c.st));
-  k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(d_solid, n_img, nx, ny, C, P.rel_residual * P.rel_residual, P.flux_balance,
-                                         (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, codes,
-                                         d_T_out, res, counter);
+  if (onchip) {
+    CoefF F;
+    for (int ph = 0; ph < 2; ph++) {
+      F.sx[ph] = (float)C.same[0][ph];
+      F.sy[ph] = (float)C.same[1][ph];
+      F.wall[ph] = (float)C.wall[ph];
+    }
+    F.dx = (float)C.diff[0];
+    F.dy = (float)C.diff[1];
+    static bool attr_set = false;
+    if (!attr_set) {
+      KB_CUDA(cudaFuncSetAttribute(k_batch2d_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
+      attr_set = true;
+    }
+    k_batch2d_onchip<<<grid, OC_THREADS, OC_SMEM, c.st>>>(d_solid, n_img, nx, ny, C, F, P.rel_residual * P.rel_residual,
+                                                          P.flux_balance, (long long)P.max_iter,
+                                                          (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, d_T_out, res,
+                                                          counter);
+  } else {
+    k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(d_solid, n_img, nx, ny, C, P.rel_residual * P.rel_residual, P.flux_balance,
+                                           (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, codes,
+                                           d_T_out, res, counter);
+  }
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
   KB_CUDA(cudaEventRecord(c.ev1, c.st));

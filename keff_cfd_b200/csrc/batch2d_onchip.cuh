@@ -1,0 +1,332 @@
+// batch2d_onchip.cuh -- the 2D batch fast path: one image per SM, the whole CG state on chip.
+//
+// A 128x128 FP64 CG needs 4 vectors x 128 KiB = 512 KiB; an SM has 227 KiB of shared memory and a
+// 256 KiB register file.  So the iteration runs in FP32 on chip and FP64 enters through RELIABLE
+// UPDATES (the mixed-precision CG used in lattice QCD solvers):
+//   * on chip (per CTA of 512 threads, 32 cells per thread in a 4(x) x 8(y) patch):
+//       p  FP32, shared memory image with zero guard rows (neighbour access for the stencil)
+//       y  FP32, shared memory: solution increment since the last reliable update
+//       1/a_P FP32, shared memory (static per image)
+//       z = r/a_P and w = (A p)/a_P  FP32, registers
+//   * in global memory (L2-resident, touched only at reliable updates): x in FP64.
+//   Every time the (recurrence) residual has dropped 10x -- and before any convergence decision --
+//   x += y is flushed in FP64, y is cleared and the TRUE residual b - A x is recomputed in FP64 with
+//   the FP64 coefficients; its rounded value replaces z.  Because y only ever holds the increment
+//   since the last flush, FP32 rounding is relative to an ever smaller quantity and the final field
+//   is FP64-accurate; every stop decision uses the FP64 true residual and FP64 wall fluxes.
+// One block-wide reduction per iteration: with z, w = D^-1 A p known before alpha,
+//   r_new.z_new = r.z - 2 alpha (z.Ap) + alpha^2 (w.Ap)
+// so p.Ap, z.Ap, w.Ap are reduced together and alpha, beta follow without touching vectors again.
+// The stencil is the same flux form as k_stencil_tma (each face conductance/flux once per patch,
+// wall = face of conductance c_wall towards 0, adiabatic face = conductance 0, folded into
+// per-thread constants); W/E neighbours come from warp shuffles, N/S rows from shared memory.
+// Replaces Keff2D/keff2D.cpp:341-471 (batch loop, SerialGS per image) for nx<=128, nx%4==0,
+// ny<=128, ny%8==0; other shapes take k_batch2d_pcg.
+#pragma once
+#include "common.cuh"
+
+namespace kb {
+
+constexpr int OC_THREADS = 512, OC_PITCH = 128, OC_ROWS = 128 + 2;
+constexpr size_t OC_SMEM =
+    (size_t)OC_ROWS * OC_PITCH * 4 + 2 * (size_t)8 * OC_THREADS * 16 + (size_t)8 * OC_THREADS * 4 + 32 * 4 * 8 + 64;
+
+struct CoefF {
+  float sx[2], sy[2], dx, dy, wall[2];
+};
+
+struct BatchOut {
+  double ql, qr, rr, bb, r1;
+  long long it;
+  int status, pad;
+};
+
+template <int N>
+__device__ __forceinline__ void block_allsum(double (&v)[N], double* red, double* bc) {
+  block_sum<N>(v, red);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int j = 0; j < N; j++) bc[j] = v[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; j++) v[j] = bc[j];
+  __syncthreads();
+}
+
+__device__ __forceinline__ float fsel(unsigned bits, float a, float b) { return bits ? a : b; }
+
+__global__ void __launch_bounds__(OC_THREADS, 1)
+    k_batch2d_onchip(const uint8_t* __restrict__ masks, int n_img, int nx, int ny, const Coef C, const CoefF F,
+                     double thr2_in, double flux_tol, long long max_iter, int const_init, double* __restrict__ xws,
+                     double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter) {
+  extern __shared__ __align__(16) unsigned char oc_smem[];
+  float* P = reinterpret_cast<float*>(oc_smem);
+  float4* Y = reinterpret_cast<float4*>(P + OC_ROWS * OC_PITCH);
+  float4* DI = Y + 8 * OC_THREADS;
+  unsigned* CW = reinterpret_cast<unsigned*>(DI + 8 * OC_THREADS);  // code bytes of my patch, one word per row
+  double* red = reinterpret_cast<double*>(CW + 8 * OC_THREADS);
+  double* bc = red + 32 * 4;
+  int* s_img = reinterpret_cast<int*>(bc + 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int x0 = lane * 4, y0 = wrp * 8;
+  const bool act = x0 < nx && y0 < ny;  // shapes are multiples of the patch: all 32 cells in or out
+  const bool wact = y0 < ny;            // warp-uniform
+  const int n = nx * ny;
+  const bool left = x0 == 0, right = x0 + 4 == nx, top = y0 == 0, bot = y0 + 8 == ny;
+  // Outward faces of the patch: wall -> conductance c_wall towards 0, adiabatic -> conductance 0
+  // (their code bits are clear by construction).  Lanes outside the image need no masking: their p,
+  // z and 1/a_P are identically 0, so whatever flux they see never reaches a sum or a stored value.
+  const float sx0 = F.sx[0], sx1 = F.sx[1], sy0 = F.sy[0], sy1 = F.sy[1], dfx = F.dx, dfy = F.dy;
+#define OC_WW(ph) ((ph) ? (left ? F.wall[1] : sx1) : (left ? F.wall[0] : sx0))
+#define OC_WE(ph) ((ph) ? (right ? F.wall[1] : sx1) : (right ? F.wall[0] : sx0))
+#define OC_CN(ph) (top ? 0.f : ((ph) ? sy1 : sy0))
+#define OC_CS(ph) (bot ? 0.f : ((ph) ? sy1 : sy0))
+
+  for (int i = tid; i < OC_ROWS * OC_PITCH; i += OC_THREADS) P[i] = 0.f;
+  float* Pown = P + (y0 + 1) * OC_PITCH + x0;  // my patch's first row inside the guarded image
+  double* xs = xws + (size_t)blockIdx.x * n;
+
+  while (true) {
+    if (tid == 0) *s_img = atomicAdd(counter, 1);
+    __syncthreads();
+    const int img = *s_img;
+    __syncthreads();
+    if (img >= n_img) break;
+    const uint8_t* m = masks + (size_t)img * n;
+    double* x64 = T_out ? T_out + (size_t)img * n : xs;
+
+    // ---- per-image setup: code bytes (registers), 1/a_P (shared), x = initial field, y = 0 ----
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      unsigned cwj = 0;
+      float4 di = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) {
+        const int yy = y0 + j;
+        float d4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int xx = x0 + i, g = yy * nx + xx;
+          const unsigned me = m[g] == 1;
+          unsigned c = me;
+          if (xx > 0 && (unsigned)(m[g - 1] == 1) != me) c |= C_W;
+          if (xx < nx - 1 && (unsigned)(m[g + 1] == 1) != me) c |= C_E;
+          if (yy < ny - 1 && (unsigned)(m[g + nx] == 1) != me) c |= C_S;
+          if (yy > 0 && (unsigned)(m[g - nx] == 1) != me) c |= C_N;
+          cwj |= c << (8 * i);
+          d4[i] = (float)(1.0 / diag_of(C, c, xx == 0, xx == nx - 1, yy == 0, yy == ny - 1, true, true));
+          x64[g] = const_init ? C.tl : C.tl + (C.tr - C.tl) * ((xx + 0.5) / nx);
+        }
+        di = make_float4(d4[0], d4[1], d4[2], d4[3]);
+      }
+      DI[j * OC_THREADS + tid] = di;
+      CW[j * OC_THREADS + tid] = cwj;
+      Y[j * OC_THREADS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    float z[8][4], w[8][4];
+    double rz = 0, rz_flush = 0, rr_true = 0, bb = 0, r1 = 0, ratio = 1, thr2 = thr2_in;
+    double ql = 0, qr = 0;
+    long long it = 0;
+    int status = 1;
+    bool first = true;
+
+    while (true) {
+      // ================= reliable update: x += y (FP64), y = 0, z = D^-1 (b - A x) in FP64 =================
+      if (!first) {
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 yv = Y[j * OC_THREADS + tid];
+            double2* xp = reinterpret_cast<double2*>(x64 + (y0 + j) * nx + x0);
+            double2 a = xp[0], b = xp[1];
+            a.x += yv.x; a.y += yv.y; b.x += yv.z; b.y += yv.w;
+            xp[0] = a; xp[1] = b;
+            Y[j * OC_THREADS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        __syncthreads();
+      }
+      double s4[4] = {0, 0, 0, 0};
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int yy = y0 + j;
+          const bool yt = yy == 0, yb = yy == ny - 1;
+          const float4 di = DI[j * OC_THREADS + tid];
+          const float dv[4] = {di.x, di.y, di.z, di.w};
+          const unsigned cwj = CW[j * OC_THREADS + tid];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int xx = x0 + i, g = yy * nx + xx;
+            const bool xl = xx == 0, xr = xx == nx - 1;
+            const unsigned c = (cwj >> (8 * i)) & 0xffu;
+            const Faces Fc = faces_of(C, c, xl, xr, yt, yb, true, true);
+            const double xc = x64[g];
+            double qv = Fc.diag * xc;
+            if (!xl) qv -= Fc.w * x64[g - 1];
+            if (!xr) qv -= Fc.e * x64[g + 1];
+            if (!yt) qv -= Fc.n * x64[g - nx];
+            if (!yb) qv -= Fc.s * x64[g + nx];
+            const double b = rhs_of(C, c, xl, xr), rv = b - qv;
+            const float zf = (float)rv * dv[i];
+            z[j][i] = zf;
+            s4[0] += rv * (double)zf;
+            s4[1] += rv * rv;
+            s4[2] += b * b;
+            s4[3] += fabs(rv);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) z[j][i] = 0.f;
+      }
+      block_allsum<4>(s4, red, bc);
+      rz = s4[0];
+      rr_true = s4[1];
+      r1 = s4[3];
+      if (first) bb = s4[2];
+      rz_flush = rz;
+      ratio = rz > 0 ? rr_true / rz : 1.0;
+      if (first) {  // p = z
+        if (act)
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            *reinterpret_cast<float4*>(Pown + j * OC_PITCH) = make_float4(z[j][0], z[j][1], z[j][2], z[j][3]);
+        first = false;
+        __syncthreads();
+      }
+      // ---- stop decisions use only FP64 quantities of the flushed field ----
+      const bool conv = !(rr_true > thr2 * bb);
+      if (conv || it >= max_iter) {
+        double f2[2] = {0, 0};
+        for (int row = tid; row < ny; row += OC_THREADS) {
+          const int l = row * nx, e = l + nx - 1;
+          f2[0] += ((m[l] == 1) ? C.wall[1] : C.wall[0]) * (x64[l] - C.tl);
+          f2[1] += ((m[e] == 1) ? C.wall[1] : C.wall[0]) * (C.tr - x64[e]);
+        }
+        block_allsum<2>(f2, red, bc);
+        ql = f2[0];
+        qr = f2[1];
+        const double keff = (ql + qr) / 2 / (C.tr - C.tl);
+        if (conv && (fabs(ql - qr) <= flux_tol * fabs(keff) || thr2 < 1e-28)) {
+          status = 0;
+          break;
+        }
+        if (it >= max_iter) break;
+        thr2 *= 1e-2;
+        if (!(rr_true > thr2 * bb)) continue;  // still satisfied: re-evaluate with the tighter target
+      }
+
+      // ================================ FP32 CG iterations ================================
+      // leave for a reliable update when the residual is down 10x or convergence is predicted
+      const double rz_stop = fmax(1e-2 * rz_flush, thr2 * bb / ratio);
+      bool broke = false;
+      while (true) {
+        float spq = 0.f, szq = 0.f, swq = 0.f;
+        if (wact) {
+          const float4 hn = *reinterpret_cast<const float4*>(Pown - OC_PITCH);
+          float4 pc = *reinterpret_cast<const float4*>(Pown);
+          float fy0, fy1, fy2, fy3;
+          {
+            const unsigned c = CW[tid];
+            fy0 = fsel(c & (C_N << 0), dfy, OC_CN(c & (C_PH << 0))) * (hn.x - pc.x);
+            fy1 = fsel(c & (C_N << 8), dfy, OC_CN(c & (C_PH << 8))) * (hn.y - pc.y);
+            fy2 = fsel(c & (C_N << 16), dfy, OC_CN(c & (C_PH << 16))) * (hn.z - pc.z);
+            fy3 = fsel(c & (C_N << 24), dfy, OC_CN(c & (C_PH << 24))) * (hn.w - pc.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 pn = *reinterpret_cast<const float4*>(Pown + (j + 1) * OC_PITCH);
+            float pw = __shfl_up_sync(0xffffffffu, pc.w, 1), pe = __shfl_down_sync(0xffffffffu, pc.x, 1);
+            if (left) pw = 0.f;
+            if (right || lane == 31) pe = 0.f;
+            const unsigned c = CW[j * OC_THREADS + tid];
+            const float a0 = fsel(c & (C_PH << 0), sx1, sx0), a1 = fsel(c & (C_PH << 8), sx1, sx0),
+                        a2 = fsel(c & (C_PH << 16), sx1, sx0);
+            const float fw = fsel(c & (C_W << 0), dfx, OC_WW(c & (C_PH << 0))) * (pc.x - pw);
+            const float f01 = fsel(c & (C_E << 0), dfx, a0) * (pc.x - pc.y);
+            const float f12 = fsel(c & (C_E << 8), dfx, a1) * (pc.y - pc.z);
+            const float f23 = fsel(c & (C_E << 16), dfx, a2) * (pc.z - pc.w);
+            const float fe = fsel(c & (C_E << 24), dfx, OC_WE(c & (C_PH << 24))) * (pc.w - pe);
+            float g0, g1, g2, g3;
+            if (j < 7) {
+              g0 = fsel(c & (C_S << 0), dfy, fsel(c & (C_PH << 0), sy1, sy0)) * (pc.x - pn.x);
+              g1 = fsel(c & (C_S << 8), dfy, fsel(c & (C_PH << 8), sy1, sy0)) * (pc.y - pn.y);
+              g2 = fsel(c & (C_S << 16), dfy, fsel(c & (C_PH << 16), sy1, sy0)) * (pc.z - pn.z);
+              g3 = fsel(c & (C_S << 24), dfy, fsel(c & (C_PH << 24), sy1, sy0)) * (pc.w - pn.w);
+            } else {
+              g0 = fsel(c & (C_S << 0), dfy, OC_CS(c & (C_PH << 0))) * (pc.x - pn.x);
+              g1 = fsel(c & (C_S << 8), dfy, OC_CS(c & (C_PH << 8))) * (pc.y - pn.y);
+              g2 = fsel(c & (C_S << 16), dfy, OC_CS(c & (C_PH << 16))) * (pc.z - pn.z);
+              g3 = fsel(c & (C_S << 24), dfy, OC_CS(c & (C_PH << 24))) * (pc.w - pn.w);
+            }
+            const float q0 = (fw + f01) + (g0 - fy0), q1 = (f12 - f01) + (g1 - fy1);
+            const float q2 = (f23 - f12) + (g2 - fy2), q3 = (fe - f23) + (g3 - fy3);
+            const float4 di = DI[j * OC_THREADS + tid];
+            w[j][0] = q0 * di.x; w[j][1] = q1 * di.y; w[j][2] = q2 * di.z; w[j][3] = q3 * di.w;
+            spq += pc.x * q0 + pc.y * q1 + pc.z * q2 + pc.w * q3;
+            szq += z[j][0] * q0 + z[j][1] * q1 + z[j][2] * q2 + z[j][3] * q3;
+            swq += w[j][0] * q0 + w[j][1] * q1 + w[j][2] * q2 + w[j][3] * q3;
+            fy0 = g0; fy1 = g1; fy2 = g2; fy3 = g3;
+            pc = pn;
+          }
+        }
+        double s3[3] = {(double)spq, (double)szq, (double)swq};
+        block_allsum<3>(s3, red, bc);
+        if (!(s3[0] > 0.0)) {  // breakdown (cannot happen for an SPD operator short of NaN)
+          status = 2;
+          broke = true;
+          break;
+        }
+        const double alpha = rz / s3[0];
+        double rzn = rz - 2.0 * alpha * s3[1] + alpha * alpha * s3[2];
+        const bool bad = !(rzn > 0.0);  // recurrence lost positivity: force a reliable update
+        if (bad) rzn = rz * 1e-2;
+        const float al = (float)alpha, be = (float)(rzn / rz);
+        rz = rzn;
+        it++;
+        if (wact) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 pv = *reinterpret_cast<const float4*>(Pown + j * OC_PITCH);
+            float4 yv = Y[j * OC_THREADS + tid];
+            z[j][0] -= al * w[j][0]; z[j][1] -= al * w[j][1]; z[j][2] -= al * w[j][2]; z[j][3] -= al * w[j][3];
+            yv.x += al * pv.x; yv.y += al * pv.y; yv.z += al * pv.z; yv.w += al * pv.w;
+            pv.x = z[j][0] + be * pv.x; pv.y = z[j][1] + be * pv.y; pv.z = z[j][2] + be * pv.z;
+            pv.w = z[j][3] + be * pv.w;
+            Y[j * OC_THREADS + tid] = yv;
+            if (act) *reinterpret_cast<float4*>(Pown + j * OC_PITCH) = pv;
+          }
+        }
+        __syncthreads();
+        if (bad || rz < rz_stop || (it & 127) == 0 || it >= max_iter) break;
+      }
+      if (broke) break;
+    }
+
+    if (tid == 0) {
+      BatchOut o;
+      o.ql = ql;
+      o.qr = qr;
+      o.rr = rr_true;
+      o.bb = bb;
+      o.r1 = r1;
+      o.it = it;
+      o.status = status;
+      o.pad = 0;
+      res[img] = o;
+    }
+    __syncthreads();
+  }
+}
+
+#undef OC_WW
+#undef OC_WE
+#undef OC_CN
+#undef OC_CS
+
+}  // namespace kb

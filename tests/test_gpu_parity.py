@@ -185,7 +185,7 @@ def test_batch_matches_single_solves_and_oracle(K):
     for r, w in zip(res, want):
         assert r["status"] == 0 and rel(r["keff"], w) < KEFF_RTOL and r["rel_residual"] <= 1e-8
     single = K.solve2d(imgs[3])
-    assert rel(res[3]["keff"], single["keff"]) < 1e-7 and np.abs(res[3]["T"] - single["T"]).max() < 1e-7
+    assert rel(res[3]["keff"], single["keff"]) < 1e-6 and np.abs(res[3]["T"] - single["T"]).max() < 1e-6
     assert np.abs(res[0]["T"] - gold_npy("discrete_img_00009_T.npy")).max() < T_ATOL
 
 
