@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(OC_THREADS, 1)
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int x0 = lane * 4, y0 = wrp * 8;
   const bool act = x0 < nx && y0 < ny;  // shapes are multiples of the patch: all 32 cells in or out
-  const bool wact = y0 < ny;            // warp-uniform
   const int n = nx * ny;
   const bool left = x0 == 0, right = x0 + 4 == nx, top = y0 == 0, bot = y0 + 8 == ny;
   // Outward faces of the patch: wall -> conductance c_wall towards 0, adiabatic -> conductance 0
@@ -227,7 +226,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1)
       bool broke = false;
       while (true) {
         float spq = 0.f, szq = 0.f, swq = 0.f;
-        if (wact) {
+        {
           const float4 hn = *reinterpret_cast<const float4*>(Pown - OC_PITCH);
           float4 pc = *reinterpret_cast<const float4*>(Pown);
           float fy0, fy1, fy2, fy3;
@@ -275,8 +274,34 @@ __global__ void __launch_bounds__(OC_THREADS, 1)
             pc = pn;
           }
         }
-        double s3[3] = {(double)spq, (double)szq, (double)swq};
-        block_allsum<3>(s3, red, bc);
+        // one barrier per reduction: FP32 inside a warp, FP64 across the 16 warps, every warp sums
+        // the 16 partials itself (fixed order -> deterministic); `red` is double-buffered by parity
+        double s3[3];
+        {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            spq += __shfl_xor_sync(0xffffffffu, spq, o);
+            szq += __shfl_xor_sync(0xffffffffu, szq, o);
+            swq += __shfl_xor_sync(0xffffffffu, swq, o);
+          }
+          double* rb = red + (it & 1) * 64;
+          if (lane == 0) {
+            rb[wrp * 4 + 0] = (double)spq;
+            rb[wrp * 4 + 1] = (double)szq;
+            rb[wrp * 4 + 2] = (double)swq;
+          }
+          __syncthreads();
+          const int l16 = lane & 15;
+          s3[0] = rb[l16 * 4 + 0];
+          s3[1] = rb[l16 * 4 + 1];
+          s3[2] = rb[l16 * 4 + 2];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            s3[0] += __shfl_xor_sync(0xffffffffu, s3[0], o);
+            s3[1] += __shfl_xor_sync(0xffffffffu, s3[1], o);
+            s3[2] += __shfl_xor_sync(0xffffffffu, s3[2], o);
+          }
+        }
         if (!(s3[0] > 0.0)) {  // breakdown (cannot happen for an SPD operator short of NaN)
           status = 2;
           broke = true;
@@ -289,7 +314,7 @@ __global__ void __launch_bounds__(OC_THREADS, 1)
         const float al = (float)alpha, be = (float)(rzn / rz);
         rz = rzn;
         it++;
-        if (wact) {
+        {
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             float4 pv = *reinterpret_cast<const float4*>(Pown + j * OC_PITCH);
