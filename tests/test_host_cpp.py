@@ -1,0 +1,148 @@
+"""The C++ drop-in shell (keff_cfd_b200/csrc/host): input.txt keys, JPG / CSV readers, output rows.
+CPU part: decoder and parsers (--check-inputs, no GPU).  GPU part: the programs end to end."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, ROOT, gold_json
+
+HOST = os.path.join(ROOT, "keff_cfd_b200", "csrc", "host")
+INPUT_2D = """Input File:
+ks: 10
+kf: 1
+MeshAmpX: {amp}
+MeshAmpY: {amp}
+InputName: {name}
+TR: 1
+TL: 0
+OutputName: batchTest.csv
+printTMap: {tmap}
+TMapName: TMAP_00001.csv
+printQMap: {tmap}
+QMapName: QMAP_00001.csv
+Convergence: 0.00001
+MaxIter: 500000
+Verbose: 1
+NumCores: 8
+MeshFlag: 0
+MaxMesh: 10
+RunBatch: {batch}
+NumImages: {nimg}
+"""
+
+
+@pytest.fixture(scope="module")
+def built():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "keff_cfd_b200", "csrc"), "all"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return HOST
+
+
+def _decode(built, path, tmp):
+    out = os.path.join(tmp, "out.raw")
+    r = subprocess.run([os.path.join(built, "jpeg2raw"), path, out], capture_output=True, text=True)
+    if r.returncode:
+        return None, r.stderr
+    hdr, raw = open(out, "rb").read().split(b"\n", 1)
+    w, h, c = map(int, hdr.split())
+    return np.frombuffer(raw, np.uint8).reshape(h, w), c
+
+
+def test_jpeg_decoder_matches_libjpeg(built, tmp_path):
+    from PIL import Image
+    from keff_cfd_b200 import structures as S
+    for f in ("00009.jpg", "00000.jpg"):     # the reference's shipped structures
+        a, c = _decode(built, os.path.join(GOLD, "inputs", f), str(tmp_path))
+        b = np.asarray(Image.open(os.path.join(GOLD, "inputs", f)))
+        assert c == 1 and np.abs(a.astype(int) - b).max() <= 1
+        assert np.array_equal(a, np.load(os.path.join(GOLD, "img_" + f[:5] + ".npy"))) or np.array_equal(a >= 150, b >= 150)
+    img = S.to_gray(S.disc_image(5, n=100))[:77, :]   # ragged size: partial MCUs
+    cases = [("L", dict(quality=95)), ("L", dict(quality=75, optimize=True)), ("RGB", dict(quality=90)),
+             ("RGB", dict(quality=90, subsampling=0)), ("L", dict(quality=95, restart_marker_blocks=4))]
+    for mode, kw in cases:
+        p = str(tmp_path / "t.jpg")
+        Image.fromarray(img).convert(mode).save(p, **kw)
+        a, c = _decode(built, p, str(tmp_path))
+        ref = np.asarray(Image.open(p).convert("L"))
+        assert a.shape == ref.shape and c == (1 if mode == "L" else 3)
+        assert np.abs(a.astype(int) - ref).max() <= 2 and np.array_equal(a >= 150, ref >= 150)
+    p = str(tmp_path / "p.jpg")
+    Image.fromarray(img).save(p, progressive=True)
+    a, msg = _decode(built, p, str(tmp_path))
+    assert a is None and "not supported" in msg
+    open(p, "wb").write(b"not a jpeg")
+    assert _decode(built, p, str(tmp_path))[0] is None
+
+
+def test_programs_parse_reference_inputs(built, tmp_path):
+    d = str(tmp_path)
+    shutil.copy(os.path.join(GOLD, "inputs", "00009.jpg"), d)
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=2, name="00009.jpg", tmap=0, batch=0, nimg=1))
+    r = subprocess.run([os.path.join(built, "keff2D"), "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # reference porosity of 00009.jpg = 0.3736572266 (its CSV row), 256 x 256 cells after MeshAmp 2
+    assert "128x128 porosity 0.3736572266 cells 65536 ks 10 kf 1 TL 0 TR 1 tol 1e-05 maxit 500000" in r.stdout
+    xyz = np.array([[1, 2, 3], [0, 0, 0], [3, 1, 2]])
+    np.savetxt(os.path.join(d, "s.csv"), xyz, fmt="%d", delimiter=",")
+    open(os.path.join(d, "in3.txt"), "w").write(
+        "Input File:\nks: 10\nkf: 1\nWidth: 4\nHeight: 4\nDepth: 4\nInputName: s.csv\nTR: 1\nTL: 0\nOutputName: o.csv\n")
+    r = subprocess.run([os.path.join(built, "keff3D"), "in3.txt", "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0 and "4x4x4 solid voxels 3" in r.stdout
+    r = subprocess.run([os.path.join(built, "keff2D"), "missing.txt"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+@pytest.mark.gpu
+def test_keff2d_program_end_to_end(built, tmp_path):
+    d = str(tmp_path)
+    shutil.copy(os.path.join(GOLD, "inputs", "00009.jpg"), d)
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name="00009.jpg", tmap=1, batch=0, nimg=1))
+    r = subprocess.run([os.path.join(built, "keff2D")], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    row = open(os.path.join(d, "batchTest.csv")).read().strip().split(",")
+    ref_row = gold_json("ref2d_00009.json")["binary_row_shipped_keys_1core"].split(",")
+    assert len(row) == len(ref_row) == 16                                  # same columns as the reference row
+    want = gold_json("discrete.json")["img_00009_amp1"]["keff"]
+    assert abs(float(row[0]) - want) / want < 1e-5
+    assert abs(float(row[1]) - float(row[2])) < 1e-4                       # QL == QR at convergence
+    assert row[4:10] == ref_row[4:10] and row[10:14] == ref_row[10:14]     # tol,name,nElements,amps,porosity,ks,kf,tl,tr
+    tm = open(os.path.join(d, "TMAP_00001.csv")).read().splitlines()
+    qm = open(os.path.join(d, "QMAP_00001.csv")).read().splitlines()
+    assert tm[0] == "x,y,T" and len(tm) == 1 + 128 * 128 and qm[0] == "x,y,Q" and len(qm) == 1 + 128 * 129
+    # x-flux through every vertical line of faces is the same at steady state (energy conservation)
+    q = np.array([float(l.split(",")[2]) for l in qm[1:]]).reshape(128, 129)
+    assert np.abs(q.sum(axis=0) - q.sum(axis=0)[0]).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_keff2d_batch_and_keff3d_programs(built, tmp_path, R):
+    from PIL import Image
+    from keff_cfd_b200 import structures as S
+    d = str(tmp_path)
+    for i in range(3):
+        Image.fromarray(S.to_gray(S.disc_image(i, n=64))).save(os.path.join(d, "%05d.jpg" % i), quality=95)
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name="x.jpg", tmap=0, batch=1, nimg=3))
+    r = subprocess.run([os.path.join(built, "keff2D")], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split(",") for l in open(os.path.join(d, "batchTest.csv")).read().strip().splitlines()]
+    assert [x[5] for x in rows] == ["00000.csv", "00001.csv", "00002.csv"]   # reference naming (keff2D.h:271)
+    for i, row in enumerate(rows):
+        want = R.orc_discrete(S.to_gray(S.disc_image(i, n=64)))["keff"]
+        assert abs(float(row[0]) - want) / want < 1e-5
+    m = S.bernoulli_volume((12, 12, 12), 0.4, 3)
+    z, y, x = np.nonzero(m)
+    np.savetxt(os.path.join(d, "vol.csv"), np.stack([x, y, z], 1), fmt="%d", delimiter=",")
+    open(os.path.join(d, "in3.txt"), "w").write(
+        "Input File:\nks: 10\nkf: 1\nWidth: 12\nHeight: 12\nDepth: 12\nMeshAmpX: 1\nMeshAmpY: 1\nMeshAmpZ: 1\n"
+        "InputName: vol.csv\nTR: 1\nTL: 0\nOutputName: out3.csv\nprintTMap: 1\nTMapName: T3.csv\nprintQMap: 0\n"
+        "Convergence: 0.00001\nMaxIter: 500000\nVerbose: 0\nNumCores: 1\nMeshFlag: 0\nRunBatch: 0\nNumImages: 1\n")
+    r = subprocess.run([os.path.join(built, "keff3D"), "in3.txt"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    row = open(os.path.join(d, "out3.csv")).read().strip().split(",")
+    want = R.orc_discrete(m)["keff"]
+    assert len(row) == 17 and abs(float(row[0]) - want) / want < 1e-5 and row[5] == "vol.csv" and row[6] == "1728"
+    t = open(os.path.join(d, "T3.csv")).read().splitlines()
+    assert t[0] == "x,y,z,T" and len(t) == 1 + 1728
