@@ -155,8 +155,9 @@ def solve2d(solid, params=None, T_init=None, want_T=True, want_q=False, device=0
 
 
 def solve2d_batch(solid, params=None, want_T=False, device=0):
-    """A batch of images u8 [n_img, ny, nx]; returns a list of per-image result dicts
-    (and the temperature maps under "T" of each when want_T)."""
+    """A batch of images u8 [n_img, ny, nx]; returns the per-image result records as a numpy
+    structured array (res[i]["keff"], res["iters"], ...), or a list of dicts that also carry the
+    temperature maps under "T" when want_T."""
     _lib.init(device)
     p = params or default_params()
     n, ny, nx = solid.shape
@@ -169,10 +170,13 @@ def solve2d_batch(solid, params=None, want_T=False, device=0):
         solid = np.ascontiguousarray(solid, dtype=np.uint8) if isinstance(solid, np.ndarray) else solid
         T = np.empty((n, ny, nx)) if want_T else None
         check(lib().keffb200_solve2d_batch(_addr(solid), n, nx, ny, C.byref(p), _addr(T), res))
-    out = [r.as_dict() for r in res]
-    if want_T:
-        for i, o in enumerate(out):
-            o["T"] = T[i]
+    # zero-copy view of the C result records: a structured array indexable as res[i]["keff"] / res["keff"]
+    table = np.ctypeslib.as_array(res).copy()
+    if not want_T:
+        return table
+    out = [{k: table[k][i].item() for k in table.dtype.names} for i in range(n)]
+    for i, o in enumerate(out):
+        o["T"] = T[i]
     return out
 
 

@@ -193,30 +193,18 @@ __global__ void __launch_bounds__(1024, 1)
   }
 }
 
-int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params& P, double* d_T_out,
-                      keffb200_result* out) {
+// Enqueue the solve of images [first, first+count) of a device-resident batch on the compute stream
+// (asynchronous).  Result records go to the device array slot of each image; counters[slot] is the
+// work counter of this launch.
+static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx, int ny, const keffb200_params& P,
+                           double* d_T_out, double* ws, uint8_t* codes, BatchOut* res, int* counters, int slot) {
   Ctx& c = ctx();
-  if (nx < 2 || ny < 2) return fail(KEFFB200_EINVAL, "image %dx%d too small", nx, ny);
-  if (P.tr == P.tl) return fail(KEFFB200_EINVAL, "TR == TL: Keff undefined");
   const size_t n = (size_t)nx * ny;
-  const int grid = std::min(n_img, c.sms);
-  const size_t need = (size_t)grid * (4 * n * 8 + n) + (size_t)n_img * sizeof(BatchOut) + 256;
-  if (need > c.cap_batch) {
-    if (c.batch_ws) cudaFree(c.batch_ws);
-    c.batch_ws = nullptr;
-    c.cap_batch = 0;
-    KB_CUDA(cudaMalloc(&c.batch_ws, need));
-    c.cap_batch = need;
-  }
-  char* base = (char*)c.batch_ws;
-  double* ws = (double*)base;
-  BatchOut* res = (BatchOut*)(base + (size_t)grid * 4 * n * 8);
-  int* counter = (int*)(res + n_img);
-  uint8_t* codes = (uint8_t*)(counter + 16);
+  const int grid = std::min(count, c.sms);
   const Coef C = make_coef(nx, ny, 1, P);
   const bool onchip = !(P.flags & KEFFB200_F_BATCH_GLOBAL) && nx <= 128 && nx % 4 == 0 && ny <= 128 && ny % 8 == 0;
-  KB_CUDA(cudaEventRecord(c.ev0, c.st));
-  KB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c.st));
+  const uint8_t* m = d_solid + (size_t)first * n;
+  double* T = d_T_out ? d_T_out + (size_t)first * n : nullptr;
   if (onchip) {
     CoefF F;
     for (int ph = 0; ph < 2; ph++) {
@@ -231,20 +219,52 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
       KB_CUDA(cudaFuncSetAttribute(k_batch2d_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
       attr_set = true;
     }
-    k_batch2d_onchip<<<grid, OC_THREADS, OC_SMEM, c.st>>>(d_solid, n_img, nx, ny, C, F, P.rel_residual * P.rel_residual,
+    k_batch2d_onchip<<<grid, OC_THREADS, OC_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual,
                                                           P.flux_balance, (long long)P.max_iter,
-                                                          (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, d_T_out, res,
-                                                          counter);
+                                                          (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, T, res + first,
+                                                          counters + slot);
   } else {
-    k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(d_solid, n_img, nx, ny, C, P.rel_residual * P.rel_residual, P.flux_balance,
-                                           (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, codes,
-                                           d_T_out, res, counter);
+    k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(m, count, nx, ny, C, P.rel_residual * P.rel_residual, P.flux_balance,
+                                           (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, codes, T,
+                                           res + first, counters + slot);
   }
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+struct BatchWs {
+  double* ws;
+  BatchOut* res;
+  int* counters;
+  uint8_t* codes;
+};
+
+static int batch2d_workspace(int n_img, int nx, int ny, BatchWs& w) {
+  Ctx& c = ctx();
+  const size_t n = (size_t)nx * ny;
+  const int grid = std::min(n_img, c.sms);
+  const size_t need = (size_t)grid * (4 * n * 8 + n) + (size_t)n_img * sizeof(BatchOut) + 256;
+  if (need > c.cap_batch) {
+    if (c.batch_ws) cudaFree(c.batch_ws);
+    c.batch_ws = nullptr;
+    c.cap_batch = 0;
+    KB_CUDA(cudaMalloc(&c.batch_ws, need));
+    c.cap_batch = need;
+  }
+  char* base = (char*)c.batch_ws;
+  w.ws = (double*)base;
+  w.res = (BatchOut*)(base + (size_t)grid * 4 * n * 8);
+  w.counters = (int*)(w.res + n_img);
+  w.codes = (uint8_t*)(w.counters + 16);
+  return 0;
+}
+
+static int batch2d_collect(const BatchWs& w, int n_img, const keffb200_params& P, keffb200_result* out) {
+  Ctx& c = ctx();
   KB_CUDA(cudaEventRecord(c.ev1, c.st));
   std::vector<BatchOut> h(n_img);
-  KB_CUDA(cudaMemcpyAsync(h.data(), res, (size_t)n_img * sizeof(BatchOut), cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaMemcpyAsync(h.data(), w.res, (size_t)n_img * sizeof(BatchOut), cudaMemcpyDeviceToHost, c.st));
   KB_CUDA(cudaStreamSynchronize(c.st));
   float ms = 0;
   KB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
@@ -260,6 +280,57 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
     o.gpu_ms = ms;  // whole-batch device time
   }
   return 0;
+}
+
+static int batch2d_check(int nx, int ny, const keffb200_params& P) {
+  if (nx < 2 || ny < 2) return fail(KEFFB200_EINVAL, "image %dx%d too small", nx, ny);
+  if (P.tr == P.tl) return fail(KEFFB200_EINVAL, "TR == TL: Keff undefined");
+  if (!(P.ks > 0) || !(P.kf > 0)) return fail(KEFFB200_EINVAL, "conductivities must be positive");
+  return 0;
+}
+
+int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params& P, double* d_T_out,
+                      keffb200_result* out) {
+  Ctx& c = ctx();
+  KB_TRY(batch2d_check(nx, ny, P));
+  BatchWs w;
+  KB_TRY(batch2d_workspace(n_img, nx, ny, w));
+  KB_CUDA(cudaEventRecord(c.ev0, c.st));
+  KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
+  KB_TRY(batch2d_enqueue(d_solid, 0, n_img, nx, ny, P, d_T_out, w.ws, w.codes, w.res, w.counters, 0));
+  return batch2d_collect(w, n_img, P, out);
+}
+
+// Host structures: the H2D copy runs on a second stream in three pieces (1/8, 3/8, 1/2 of the batch)
+// and each piece's solve waits only for its own copy, so all but the first 1/8 of the transfer hides
+// behind compute.  d_stage: device staging buffer for the whole batch.
+int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int nx, int ny, const keffb200_params& P,
+                       double* d_T_out, keffb200_result* out) {
+  Ctx& c = ctx();
+  KB_TRY(batch2d_check(nx, ny, P));
+  BatchWs w;
+  KB_TRY(batch2d_workspace(n_img, nx, ny, w));
+  const size_t n = (size_t)nx * ny;
+  int cut[4] = {0, n_img / 8, n_img / 2, n_img};
+  if (n_img < 4 * c.sms) cut[1] = cut[2] = 0;  // small batches: one piece
+  KB_CUDA(cudaEventRecord(c.ev0, c.st));
+  KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
+  KB_CUDA(cudaEventRecord(c.evx, c.st));
+  KB_CUDA(cudaStreamWaitEvent(c.st2, c.evx, 0));  // staging buffer free (previous call's kernels are done)
+  for (int k = 0; k < 3; k++) {
+    const int first = cut[k], count = cut[k + 1] - cut[k];
+    if (count <= 0) continue;
+    KB_CUDA(cudaMemcpyAsync(d_stage + (size_t)first * n, h_solid + (size_t)first * n, (size_t)count * n,
+                            cudaMemcpyHostToDevice, c.st2));
+    KB_CUDA(cudaEventRecord(c.evp[k], c.st2));
+  }
+  for (int k = 0; k < 3; k++) {
+    const int first = cut[k], count = cut[k + 1] - cut[k];
+    if (count <= 0) continue;
+    KB_CUDA(cudaStreamWaitEvent(c.st, c.evp[k], 0));
+    KB_TRY(batch2d_enqueue(d_stage, first, count, nx, ny, P, d_T_out, w.ws, w.codes, w.res, w.counters, k));
+  }
+  return batch2d_collect(w, n_img, P, out);
 }
 
 }  // namespace kb

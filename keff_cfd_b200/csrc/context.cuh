@@ -42,7 +42,7 @@ struct Ctx {
   bool ready = false;
   int device = -1, sms = 0;
   cudaStream_t st = nullptr, st2 = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx = nullptr, evy = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx = nullptr, evy = nullptr, evp[3] = {nullptr, nullptr, nullptr};
   PFN_encodeTiled encode = nullptr;
   long launches = 0;
   std::string err;
@@ -58,6 +58,10 @@ struct Ctx {
   // batch workspace
   size_t cap_batch = 0;
   void* batch_ws = nullptr;
+  size_t cap_stage = 0;  // host-path staging of image batches (+ their temperature maps)
+  uint8_t* stage = nullptr;
+  size_t cap_stageT = 0;
+  double* stageT = nullptr;
   Nccl nccl;
   bool dist_active = false;  // true only inside a slab solve: halo exchange + all-reduces enabled
 };

@@ -13,6 +13,8 @@ namespace kb {
 // batch2d.cu
 int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params& P, double* d_T_out,
                       keffb200_result* out);
+int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int nx, int ny, const keffb200_params& P,
+                       double* d_T_out, keffb200_result* out);
 
 static keffb200_params norm_params(const keffb200_params* p) {
   keffb200_params P;
@@ -420,6 +422,7 @@ int keffb200_init(int device) {
   KB_CUDA(cudaEventCreate(&c.ev1));
   KB_CUDA(cudaEventCreateWithFlags(&c.evx, cudaEventDisableTiming));
   KB_CUDA(cudaEventCreateWithFlags(&c.evy, cudaEventDisableTiming));
+  for (int k = 0; k < 3; k++) KB_CUDA(cudaEventCreateWithFlags(&c.evp[k], cudaEventDisableTiming));
   KB_CUDA(cudaMalloc(&c.partials, (size_t)PARTIAL_SLOTS * 3 * sizeof(double)));
   KB_CUDA(cudaMalloc(&c.S, sizeof(Scal)));
   KB_CUDA(cudaMallocHost(&c.hS, sizeof(Scal)));
@@ -448,6 +451,12 @@ void keffb200_shutdown(void) {
   if (c.code) cudaFree(c.code);
   if (c.mask) cudaFree(c.mask);
   if (c.batch_ws) cudaFree(c.batch_ws);
+  if (c.stage) cudaFree(c.stage);
+  if (c.stageT) cudaFree(c.stageT);
+  c.stage = nullptr;
+  c.stageT = nullptr;
+  c.cap_stage = c.cap_stageT = 0;
+  for (int k = 0; k < 3; k++) cudaEventDestroy(c.evp[k]);
   if (c.S) cudaFree(c.S);
   if (c.hS) cudaFreeHost(c.hS);
   c.code = c.mask = nullptr;
@@ -532,25 +541,26 @@ int keffb200_solve2d_batch(const uint8_t* solid, int n_img, int nx, int ny, cons
   if (!solid || !out || n_img < 1) return fail(KEFFB200_EINVAL, "bad argument");
   Ctx& c = ctx();
   const size_t n = (size_t)nx * ny, tot = n * n_img;
-  uint8_t* dm = nullptr;
-  double* dT = nullptr;
-  KB_CUDA(cudaMalloc(&dm, tot));
-  if (T_out && cudaMalloc(&dT, tot * 8) != cudaSuccess) {
-    cudaFree(dm);
-    return fail(KEFFB200_ENOMEM, "cannot allocate batch temperature output");
+  if (tot > c.cap_stage) {
+    if (c.stage) cudaFree(c.stage);
+    c.stage = nullptr;
+    c.cap_stage = 0;
+    KB_CUDA(cudaMalloc(&c.stage, tot));
+    c.cap_stage = tot;
   }
-  int rc = 0;
-  if (cudaMemcpyAsync(dm, solid, tot, cudaMemcpyHostToDevice, c.st) != cudaSuccess)
-    rc = fail(KEFFB200_ECUDA, "H2D copy of the image batch failed");
-  if (!rc) rc = batch2d_solve_dev(dm, n_img, nx, ny, norm_params(p), dT, out);
-  if (!rc && T_out) {
-    if (cudaMemcpyAsync(T_out, dT, tot * 8, cudaMemcpyDeviceToHost, c.st) != cudaSuccess ||
-        cudaStreamSynchronize(c.st) != cudaSuccess)
-      rc = fail(KEFFB200_ECUDA, "D2H copy of the temperature maps failed");
+  if (T_out && tot > c.cap_stageT) {
+    if (c.stageT) cudaFree(c.stageT);
+    c.stageT = nullptr;
+    c.cap_stageT = 0;
+    if (cudaMalloc(&c.stageT, tot * 8) != cudaSuccess) return fail(KEFFB200_ENOMEM, "cannot allocate batch temperature output");
+    c.cap_stageT = tot;
   }
-  cudaFree(dm);
-  if (dT) cudaFree(dT);
-  return rc;
+  KB_TRY(batch2d_solve_host(solid, c.stage, n_img, nx, ny, norm_params(p), T_out ? c.stageT : nullptr, out));
+  if (T_out) {
+    KB_CUDA(cudaMemcpyAsync(T_out, c.stageT, tot * 8, cudaMemcpyDeviceToHost, c.st));
+    KB_CUDA(cudaStreamSynchronize(c.st));
+  }
+  return 0;
 }
 
 // ---- pieces ------------------------------------------------------------------------------------
