@@ -203,6 +203,21 @@ def test_batch_is_schedule_independent_and_handles_ragged_counts(K):
         assert rel(rr[i]["keff"], K.solve2d(rect[i])["keff"]) < 1e-6   # two solvers, each at relres 1e-8
 
 
+@pytest.mark.parametrize("shape", [(32, 32), (64, 64), (48, 64), (128, 64), (64, 128), (16, 128), (128, 16), (96, 112),
+                                   (40, 36), (8, 4)])
+def test_onchip_batch_shapes_against_fp64_batch(K, shape):
+    """Every image shape the on-chip kernel accepts (with and without the coarse level, partial warps,
+    partial lanes) against the all-FP64 global-memory kernel."""
+    from keff_cfd_b200 import structures as S
+    ny, nx = shape
+    imgs = np.stack([S.disc_image(i, n=128)[:ny, :nx] for i in range(5)])
+    fast = K.solve2d_batch(imgs)
+    slow = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_GLOBAL))
+    for f, s in zip(fast, slow):
+        assert f["status"] == 0 and s["status"] == 0 and f["rel_residual"] <= 1e-8
+        assert rel(f["keff"], s["keff"]) < 1e-6
+
+
 def test_onchip_mixed_precision_batch_equals_fp64_batch(K):
     """The on-chip FP32 + FP64-reliable-update kernel against the all-FP64 global-memory kernel."""
     from keff_cfd_b200 import structures as S
