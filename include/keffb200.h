@@ -49,6 +49,9 @@ typedef struct keffb200_params {
 #define KEFFB200_F_NO_TMA 1      /* use the plain global-load stencil kernel (debug / odd nx) */
 #define KEFFB200_F_BATCH_GLOBAL 4 /* 2D batches: force the global-memory FP64 kernel (the on-chip
                                     mixed-precision kernel is used when nx<=128, nx%4==0, ny<=128, ny%8==0) */
+#define KEFFB200_F_NO_MG 8       /* grid solver: plain diagonally preconditioned CG instead of the
+                                    multigrid-preconditioned one (used anyway when nx is odd, the
+                                    grid has fewer than 65 cells, ny < 2, or the volume is z-slabbed) */
 #define KEFFB200_F_ZERO_INIT 2   /* start from T = tl everywhere (the reference's actual T0,
                                     Keff2D/keff2D.h:584-611) instead of the linear ramp */
 
@@ -125,6 +128,12 @@ int keffb200_apply(const uint8_t* solid, int nx, int ny, int nz, const keffb200_
  * energy-imbalance Residual() (Keff2D/keff2D.h:384-424) of a given host field T. */
 int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T,
                   double* qL, double* qR, keffb200_result* out);
+/* z = M r: one application of the multigrid V-cycle that preconditions the grid solver's CG (no
+ * reference counterpart; exposed so tests can check that M is symmetric positive definite and what
+ * it does to the spectrum).  Host buffers of nx*ny*nz doubles; fails with KEFFB200_EINVAL for grids
+ * the multigrid path does not take (see KEFFB200_F_NO_MG). */
+int keffb200_precond(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* r,
+                     double* z);
 /* Timing hook: `reps` applications of the stencil kernel on device-resident data
  * (one cell-update per cell per application, 16 B/cell of compulsory traffic).  Returns the average
  * milliseconds per application, measured with CUDA events on the launching stream. */

@@ -30,6 +30,7 @@ class Result(C.Structure):
 F_NO_TMA = 1
 F_ZERO_INIT = 2
 F_BATCH_GLOBAL = 4
+F_NO_MG = 8
 COMM_ID_BYTES = 128
 
 # every symbol include/keffb200.h declares (tests check the built library exports each of them)
@@ -38,7 +39,7 @@ EXPORTS = [
     "keffb200_default_params", "keffb200_launch_count", "keffb200_solve2d", "keffb200_solve2d_batch",
     "keffb200_solve3d", "keffb200_solve3d_dev", "keffb200_solve2d_batch_dev", "keffb200_comm_id",
     "keffb200_dist_init", "keffb200_dist_shutdown", "keffb200_solve3d_slab_dev", "keffb200_apply",
-    "keffb200_flux", "keffb200_bench_apply_dev", "keffb200_gen_bernoulli_dev",
+    "keffb200_flux", "keffb200_bench_apply_dev", "keffb200_gen_bernoulli_dev", "keffb200_precond",
 ]
 
 _lib = None
@@ -74,6 +75,7 @@ def lib():
         L.keffb200_solve3d_slab_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, PP, dp, RP]
         L.keffb200_apply.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, dp]
         L.keffb200_flux.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp, dp, RP]
+        L.keffb200_precond.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp]
         L.keffb200_bench_apply_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, C.c_int,
                                                C.POINTER(C.c_float)]
         L.keffb200_gen_bernoulli_dev.argtypes = [u8p, C.c_size_t, C.c_ulonglong, C.c_ulonglong, C.c_double]

@@ -195,6 +195,20 @@ def apply_operator(solid, x, params=None, want_b=False, device=0):
     return (y, b) if want_b else y
 
 
+def precondition(solid, r, params=None, device=0):
+    """z = M r: one multigrid V-cycle of the grid solver's preconditioner (test hook)."""
+    _lib.init(device)
+    p = params or default_params()
+    solid = np.ascontiguousarray(solid, dtype=np.uint8)
+    if solid.ndim == 2:
+        solid = solid[None]
+    nz, ny, nx = solid.shape
+    r = np.ascontiguousarray(r, dtype=np.float64).reshape(nz, ny, nx)
+    z = np.empty_like(r)
+    check(lib().keffb200_precond(_addr(solid), nx, ny, nz, C.byref(p), _addr(r), _addr(z)))
+    return z
+
+
 def boundary_flux(solid, T, params=None, device=0):
     """Flux integration + energy residual of a given field (Keff2D/keff2D.cpp:151-170, keff2D.h:384)."""
     _lib.init(device)

@@ -49,6 +49,11 @@ struct Ctx {
   // grid-solver workspace (grow-only)
   size_t cap_field = 0;  // doubles per field incl. halo planes
   double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr;
+  double* z = nullptr;   // preconditioned residual of the multigrid path (no halo planes)
+  size_t cap_z = 0;
+  float* mg_pool = nullptr;  // stored multigrid levels (grow-only)
+  size_t cap_mg = 0;         // floats
+  double* mg_inv = nullptr;  // dense inverse of the coarsest level
   uint8_t *code = nullptr, *mask = nullptr;
   size_t cap_aux = 0;  // doubles in qL/qR
   double *qL = nullptr, *qR = nullptr;

@@ -423,9 +423,10 @@ __global__ void __launch_bounds__(256) k_cg_dir(double* __restrict__ p, const do
 //       2 -> INIT {r.z, r.r, b.b} (stride 3) into S->tmp[0..2]
 //       3 -> RESID {-, r.r, |r|1} (stride 3) into S->tmp[1..2]
 //       4 -> flux {QL, QR} (stride 2) into S->tmp[0..1]
+//       5 -> r.z of the multigrid post pass (stride 3, slot 0) into S->tmp[0]
 __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int n, int what, Scal* S) {
   __shared__ double red[32 * 3];
-  if (S->done && what <= 1) return;
+  if (S->done && (what <= 1 || what == 5)) return;
   const int stride = (what == 1 || what == 4) ? 2 : 3;
   double acc[3] = {0, 0, 0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ pa
   block_sum<3>(acc, red);
   if (threadIdx.x == 0) {
     if (what == 0) S->pq = acc[0];
+    else if (what == 5) S->tmp[0] = acc[0];
     else if (what == 3) { S->tmp[1] = acc[1]; S->tmp[2] = acc[2]; }
     else { S->tmp[0] = acc[0]; S->tmp[1] = acc[1]; S->tmp[2] = acc[2]; }
   }

@@ -7,6 +7,7 @@
 // only reads a 150-byte scalar record every `check_every` iterations.
 #include "context.cuh"
 #include "kernels.cuh"
+#include "mg.cuh"
 
 namespace kb {
 
@@ -64,6 +65,13 @@ static int ensure_ws(const Dom& D) {
     KB_CUDA(cudaMalloc(&c.code, need));
     KB_CUDA(cudaMalloc(&c.mask, need));
     c.cap_field = need;
+  }
+  if (plane * D.nz > c.cap_z) {
+    if (c.z) cudaFree(c.z);
+    c.z = nullptr;
+    c.cap_z = 0;
+    KB_CUDA(cudaMalloc(&c.z, plane * D.nz * sizeof(double)));
+    c.cap_z = plane * D.nz;
   }
   const size_t rows = (size_t)D.ny * D.nz;
   if (rows > c.cap_aux) {
@@ -201,6 +209,166 @@ static int stencil_launch(const Stencil& s, int which, double* o0, double* o1) {
   return 0;
 }
 
+
+// ---- multigrid preconditioner: hierarchy, plan, V-cycle -----------------------------------------
+struct Mg {
+  bool on = false;
+  int nlev = 0;                // stored levels 1..nlev; level nlev is the dense one
+  MgLevel L[MG_MAX_LEVELS];    // L[0]: extent and coarsening flags of the voxel grid only
+  int ndense = 0;
+  CUtensorMap tm_r;
+  Plan plan{};
+  int grid = 0;
+  double omega = 0.9;
+  Dom D{};
+  Coef C{};
+};
+
+static bool mg_eligible(const Dom& D, int flags) {
+  return !(flags & (KEFFB200_F_NO_MG | KEFFB200_F_NO_TMA)) && D.nx % 2 == 0 && D.nx >= 4 && D.ny >= 2 &&
+         (long)D.nx * D.ny * D.nz > MG_DENSE_MAX && !ctx().dist_active && ctx().encode != nullptr;
+}
+
+static int mg_grid(long n) { return (int)std::max<long>(1, std::min<long>((n + 255) / 256, (long)ctx().sms * 8)); }
+
+static MgLevelView mg_view(const MgLevel& L) { return MgLevelView{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.dinv}; }
+
+static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
+  Ctx& c = ctx();
+  mg.D = D;
+  mg.C = C;
+  // extents
+  int nx = D.nx, ny = D.ny, nz = D.nz, l = 0;
+  size_t floats = 0;
+  while (true) {
+    MgLevel& L = mg.L[l];
+    L.nx = nx;
+    L.ny = ny;
+    L.nz = nz;
+    L.fx = nx > 1;
+    L.fy = ny > 1;
+    L.fz = nz > 1;
+    if (l > 0) floats += 7 * (((size_t)nx * ny * (nz + 2) + 31) / 32 * 32);
+    if (l > 0 && (long)nx * ny * nz <= MG_DENSE_MAX) break;
+    if (l + 1 >= MG_MAX_LEVELS) return fail(KEFFB200_EINVAL, "multigrid hierarchy too deep");
+    nx = (nx + 1) / 2;
+    ny = (ny + 1) / 2;
+    nz = (nz + 1) / 2;
+    l++;
+  }
+  mg.nlev = l;
+  mg.ndense = mg.L[l].nx * mg.L[l].ny * mg.L[l].nz;
+  if (floats > c.cap_mg) {
+    if (c.mg_pool) cudaFree(c.mg_pool);
+    c.mg_pool = nullptr;
+    c.cap_mg = 0;
+    KB_CUDA(cudaMalloc(&c.mg_pool, floats * sizeof(float)));
+    c.cap_mg = floats;
+  }
+  if (!c.mg_inv) KB_CUDA(cudaMalloc(&c.mg_inv, (size_t)MG_DENSE_MAX * MG_DENSE_MAX * sizeof(double)));
+  KB_CUDA(cudaMemsetAsync(c.mg_pool, 0, floats * sizeof(float), c.st));
+  float* base = c.mg_pool;
+  for (int k = 1; k <= mg.nlev; k++) {
+    MgLevel& L = mg.L[k];
+    const size_t plane = (size_t)L.nx * L.ny, stride = (plane * (L.nz + 2) + 31) / 32 * 32;
+    float** arr[7] = {&L.cx, &L.cy, &L.cz, &L.wsum, &L.dinv, &L.b, &L.e};
+    for (int a = 0; a < 7; a++) {
+      *arr[a] = base + plane;  // plane 0 (one spare plane below)
+      base += stride;
+    }
+  }
+  // operators
+  {
+    const MgLevel& L0 = mg.L[0];
+    MgLevel& L1 = mg.L[1];
+    k_mg_coarsen_fine<<<mg_grid((long)L1.nx * L1.ny * L1.nz), 256, 0, c.st>>>(c.code, C, D, L0.fx, L0.fy, L0.fz, L1);
+    KB_LAUNCHED();
+  }
+  for (int k = 1; k <= mg.nlev; k++) {
+    MgLevel& L = mg.L[k];
+    if (k > 1) {
+      k_mg_coarsen_level<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(mg.L[k - 1], L);
+      KB_LAUNCHED();
+    }
+    k_mg_dinv<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(L, 0);
+    KB_LAUNCHED();
+  }
+  k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.L[mg.nlev], c.mg_inv);
+  KB_LAUNCHED();
+  KB_CUDA(cudaGetLastError());
+  // voxel-grid passes: tensor map on r, work plan (z chunks of even length so aggregates stay whole)
+  KB_TRY(make_tmap(&mg.tm_r, c.r, D));
+  static bool attr_done = false;
+  if (!attr_done) {
+    KB_CUDA(cudaFuncSetAttribute(k_mg_fine<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    KB_CUDA(cudaFuncSetAttribute(k_mg_fine<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    attr_done = true;
+  }
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_fine<1>, NTHR, MG_SMEM);
+  occ = std::max(occ, 1);
+  const int G = c.sms * occ;
+  Plan pl;
+  pl.ntx = (D.nx + TX - 1) / TX;
+  pl.nty = (D.ny + TY - 1) / TY;
+  const long tiles = (long)pl.ntx * pl.nty;
+  long best_cost = -1;
+  int best_zlen = D.nz;
+  for (int nzc = 1; nzc <= std::max(1, D.nz / 4); nzc++) {
+    int zlen = (D.nz + nzc - 1) / nzc;
+    if (zlen & 1) zlen++;
+    const int real_nzc = (D.nz + zlen - 1) / zlen;
+    const long items = tiles * real_nzc;
+    const long per_cta = (items + G - 1) / G;
+    const long cost = per_cta * (zlen + 2 + 8);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_zlen = zlen;
+    }
+  }
+  pl.zlen = best_zlen;
+  pl.nzc = (D.nz + pl.zlen - 1) / pl.zlen;
+  pl.nitems = (int)(tiles * pl.nzc);
+  mg.plan = pl;
+  mg.grid = (int)std::min<long>(std::min<long>(pl.nitems, G), PARTIAL_SLOTS);
+  mg.on = true;
+  return 0;
+}
+
+// z = M r  (r: plane 0 of a field with zeroed halo planes; partial r.z lands in ctx().partials, stride 3)
+static int mg_vcycle(const Mg& mg, const double* r, double* z) {
+  Ctx& c = ctx();
+  const float om = (float)mg.omega;
+  const MgLevel& L0 = mg.L[0];
+  const MgLevel& L1 = mg.L[1];
+  MgFine mf{L1.e, L1.b, L1.nx, L1.ny, L0.fy, L0.fz, mg.omega};
+  k_mg_fine<0><<<mg.grid, NTHR, MG_SMEM, c.st>>>(mg.tm_r, r, c.code, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
+  KB_LAUNCHED();
+  for (int k = 1; k < mg.nlev; k++) {
+    const MgLevel& L = mg.L[k];
+    const MgLevel& N = mg.L[k + 1];
+    k_mg_pre<<<mg_grid((long)N.nx * N.ny * N.nz), 256, 0, c.st>>>(mg_view(L), L.b, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
+                                                                   N.b, om, 0, 0, c.S);
+    KB_LAUNCHED();
+  }
+  {
+    const MgLevel& L = mg.L[mg.nlev];
+    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, L.b, L.e, mg.ndense, c.S);
+    KB_LAUNCHED();
+  }
+  for (int k = mg.nlev - 1; k >= 1; k--) {
+    const MgLevel& L = mg.L[k];
+    const MgLevel& N = mg.L[k + 1];
+    k_mg_post<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(mg_view(L), L.b, N.e, L.fx, L.fy, L.fz, N.nx, N.ny,
+                                                                    L.e, om, 0, 0, c.S);
+    KB_LAUNCHED();
+  }
+  k_mg_fine<1><<<mg.grid, NTHR, MG_SMEM, c.st>>>(mg.tm_r, r, c.code, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
+  KB_LAUNCHED();
+  KB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int vec_threads(int nx, int V) {
   const int lanes = (nx + V - 1) / V;
   return std::min(256, std::max(32, (lanes + 31) / 32 * 32));
@@ -243,6 +411,15 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   }
   Stencil s;
   KB_TRY(stencil_setup(s, D, C, P.flags));
+  Mg mg;
+  if (mg_eligible(D, P.flags)) {
+    KB_CUDA(cudaMemsetAsync(c.r, 0, plane * 8, c.st));
+    KB_CUDA(cudaMemsetAsync(c.r + plane * (D.nz + 1), 0, plane * 8, c.st));
+    KB_TRY(mg_setup(mg, D, C));
+  }
+  const long n2 = (long)(n / 2);
+  const int gm = mg_grid(n2);
+  const long check_every = mg.on ? std::min<long>(P.check_every, 4) : P.check_every;
 
   Scal h0;
   memset(&h0, 0, sizeof h0);
@@ -265,10 +442,19 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       KB_TRY(allreduce_tmp(c.S->tmp, 3));
       k_step_init<<<1, 1, 0, c.st>>>(c.S);
       KB_LAUNCHED();
+      if (mg.on) {  // p = z = M r, r.z
+        KB_TRY(mg_vcycle(mg, r, c.z));
+        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
+        KB_LAUNCHED();
+        k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, 0);
+        KB_LAUNCHED();
+        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(p, c.z, n2, (long)n, c.S, 0, 1);
+        KB_LAUNCHED();
+      }
       need_init = false;
       k = 0;
     }
-    const long batch = std::min<long>(P.check_every, P.max_iter - total_iters - k);
+    const long batch = std::min<long>(check_every, P.max_iter - total_iters - k);
     for (long i = 0; i < batch; i++, k++) {
       const int par = (int)(k & 1);
       KB_TRY(exchange_halo(c.p, D, c.st));
@@ -276,6 +462,22 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 0, c.S);
       KB_LAUNCHED();
       KB_TRY(allreduce_tmp(&c.S->pq, 1));
+      if (mg.on) {
+        k_cg_update_mg<<<gm, 256, 0, c.st>>>(x, r, p, q, n2, (long)n, c.S, par, c.partials);
+        KB_LAUNCHED();
+        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gm, 1, c.S);
+        KB_LAUNCHED();
+        k_step_mg_rr<<<1, 1, 0, c.st>>>(c.S);
+        KB_LAUNCHED();
+        KB_TRY(mg_vcycle(mg, r, c.z));
+        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
+        KB_LAUNCHED();
+        k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, par ^ 1);
+        KB_LAUNCHED();
+        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(p, c.z, n2, (long)n, c.S, par, 0);
+        KB_LAUNCHED();
+        continue;
+      }
       if (V == 2) k_cg_update<2><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
       else k_cg_update<1><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
       KB_LAUNCHED();
@@ -450,6 +652,13 @@ void keffb200_shutdown(void) {
   }
   if (c.code) cudaFree(c.code);
   if (c.mask) cudaFree(c.mask);
+  if (c.z) cudaFree(c.z);
+  if (c.mg_pool) cudaFree(c.mg_pool);
+  if (c.mg_inv) cudaFree(c.mg_inv);
+  c.z = nullptr;
+  c.mg_pool = nullptr;
+  c.mg_inv = nullptr;
+  c.cap_z = c.cap_mg = 0;
   if (c.batch_ws) cudaFree(c.batch_ws);
   if (c.stage) cudaFree(c.stage);
   if (c.stageT) cudaFree(c.stageT);
@@ -633,6 +842,31 @@ int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_p
   out->keff = (c.hS->ql + c.hS->qr) / 2 / (P.tr - P.tl);
   out->energy_residual = c.hS->tmp[2];
   out->rel_residual = sqrt(c.hS->tmp[1]);  // absolute 2-norm here: no ||b|| without an INIT pass
+  return 0;
+}
+
+int keffb200_precond(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* rin,
+                     double* zout) {
+  KB_TRY(need_ready());
+  if (!solid || !rin || !zout) return fail(KEFFB200_EINVAL, "null argument");
+  Ctx& c = ctx();
+  const keffb200_params P = norm_params(p);
+  Dom D{nx, ny, nz, 0, nz};
+  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
+  if (!mg_eligible(D, P.flags)) return fail(KEFFB200_EINVAL, "grid %dx%dx%d does not take the multigrid path", nx, ny, nz);
+  KB_TRY(stage_mask(solid, false, D));
+  const size_t plane = (size_t)nx * ny, n = plane * nz;
+  const Coef C = make_coef(nx, ny, nz, P);
+  k_make_code<<<c.sms * 8, 256, 0, c.st>>>(c.mask + plane, c.code, D, 0, 0);
+  KB_LAUNCHED();
+  KB_CUDA(cudaMemsetAsync(c.r, 0, plane * (nz + 2) * 8, c.st));
+  KB_CUDA(cudaMemcpyAsync(c.r + plane, rin, n * 8, cudaMemcpyHostToDevice, c.st));
+  KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
+  Mg mg;
+  KB_TRY(mg_setup(mg, D, C));
+  KB_TRY(mg_vcycle(mg, c.r + plane, c.z));
+  KB_CUDA(cudaMemcpyAsync(zout, c.z, n * 8, cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
   return 0;
 }
 

@@ -170,8 +170,11 @@ def test_argument_errors(K):
         K.solve2d(m, K.default_params(ks=-1.0))
     r = _lib.Result()
     assert _lib.lib().keffb200_solve2d(None, 4, 4, None, None, None, None, None, ctypes.byref(r)) == -2
-    capped = K.solve2d(K.structure_from_image(gold_npy("img_00009.npy")), K.default_params(max_iter=64))
-    assert capped["status"] == 1 and capped["iters"] == 64          # MaxIter honoured
+    img = K.structure_from_image(gold_npy("img_00009.npy"))
+    capped = K.solve2d(img, K.default_params(max_iter=64, flags=K.F_NO_MG))
+    assert capped["status"] == 1 and capped["iters"] == 64          # MaxIter honoured (plain CG)
+    capped = K.solve2d(img, K.default_params(max_iter=6))
+    assert capped["status"] == 1 and capped["iters"] == 6           # ... and by the multigrid path
 
 
 # ------------------------------------------------------------------------------ batches (config 2)
