@@ -338,31 +338,62 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
         tma_load_3d(raw + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + issued);
       }
     }
+    // Staging assignment: thread t owns row t/14 of the 68x18 box and the cells tc, tc+14, .. tc+56 of
+    // it (tc = t%14), so every global address is one base register plus an immediate.
+    const int tr = tid / 14, tc = tid - tr * 14;
+    const int sy = yo - 1 + tr, sx = xo - 2 + tc;
+    const bool rowok = tid < 252 && sy >= 0 && sy < D.ny;
+    unsigned vmask = 0, smask = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const int x = sx + 14 * i;
+      if (rowok && tc + 14 * i < BOXW && x >= 0 && x < D.nx) vmask |= 1u << i;
+      if (sy == 0 || sy == D.ny - 1 || x == 0 || x == D.nx - 1) smask |= 1u << i;
+    }
+    const long cbase = (long)sy * D.nx + sx;
+    const long ebase = POST ? (long)(M.fy ? sy >> 1 : sy) * M.nx1 + (sx >> 1) : 0;
+    const int ubase = tr * BOXW + tc;
+    unsigned pc[5];  // code bytes of the plane staged next, fetched one step ahead
+    float pe[5];     // (POST) level-1 corrections of the same cells
+    auto prefetch = [&](int j) {
+      const int lz = zb - 1 + j;
+      if (lz < 0 || lz >= D.nz) return;
+      const uint8_t* cp = code + (long)lz * plane + cbase;
+      const float* ep = POST ? M.e1 + (long)(M.fz ? lz >> 1 : lz) * M.ny1 * M.nx1 + ebase : nullptr;
+#pragma unroll
+      for (int i = 0; i < 5; i++)
+        if (vmask >> i & 1u) {
+          pc[i] = cp[14 * i];
+          if (POST) pe[i] = ep[7 * i];
+        }
+    };
     // plane j of the item (local plane zb-1+j)  ->  U ring slot j & 3
     auto transform = [&](int j) {
       const uint32_t sq = seq + j, st = sq % MG_NST;
       mbar_wait(&full[st], (sq / MG_NST) & 1);
-      const double* src = reinterpret_cast<const double*>(raw + st * STAGE_STRIDE);
-      double* dst = U + (j & (MG_NU - 1)) * MG_UPLANE;
+      const double* src = reinterpret_cast<const double*>(raw + st * STAGE_STRIDE) + ubase;
+      double* dst = U + (j & (MG_NU - 1)) * MG_UPLANE + ubase;
       const int lz = zb - 1 + j;
       const bool zin = lz >= 0 && lz < D.nz;
       const bool zsurf = !flat && (D.z0 + lz == 0 || D.z0 + lz == D.nzg - 1);
-      const long zoff = (long)lz * plane;
-      const long eoff = POST ? (long)(M.fz ? lz >> 1 : lz) * M.ny1 * M.nx1 : 0;
-      for (int cidx = tid; cidx < MG_UPLANE; cidx += NTHR) {
-        const int by = cidx / BOXW, bx = cidx - by * BOXW;
-        const int x = xo - 2 + bx, y = yo - 1 + by;
-        double u = 0.0;
-        if (zin && x >= 0 && x < D.nx && y >= 0 && y < D.ny) {
-          const unsigned cc = code[zoff + (long)y * D.nx + x];
-          const bool surf = zsurf || x == 0 || x == D.nx - 1 || y == 0 || y == D.ny - 1;
-          const double di = surf ? mg_dinv_exact(C, D, cc, x, y, lz) : tab[cc & 127u];
-          u = om * src[cidx] * di;
-          if (POST) u += (double)M.e1[eoff + (long)(M.fy ? y >> 1 : y) * M.nx1 + (x >> 1)];
+      double u[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        u[i] = 0.0;
+        if (zin && (vmask >> i & 1u)) {
+          const double di = (zsurf || (smask >> i & 1u)) ? mg_dinv_exact(C, D, pc[i], sx + 14 * i, sy, lz) : tab[pc[i] & 127u];
+          u[i] = om * src[14 * i] * di;
+          if (POST) u[i] += (double)pe[i];
         }
-        dst[cidx] = u;
+      }
+      if (j + 1 < nplanes) prefetch(j + 1);
+      if (tid < 252) {
+#pragma unroll
+        for (int i = 0; i < 5; i++)
+          if (tc + 14 * i < BOXW) dst[14 * i] = u[i];
       }
     };
+    prefetch(0);
     transform(0);
     transform(1);
     if (nplanes > 2) transform(2);
