@@ -286,9 +286,8 @@ struct MgFine {
   double omega;
 };
 
-__device__ __forceinline__ double mg_dinv_exact(const Coef& C, const Dom& D, unsigned c, int x, int y, int lz) {
-  return 1.0 / diag_of(C, c, x == 0, x == D.nx - 1, y == 0, y == D.ny - 1, D.z0 + lz == 0, D.z0 + lz == D.nzg - 1);
-}
+// position class of a cell along one axis: 0 interior, 1 first, 2 last
+__device__ __forceinline__ int mg_cls(int i, int n) { return i == 0 ? 1 : (i == n - 1 ? 2 : 0); }
 
 template <int POST>
 __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUtensorMap tm,
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
                                                      double* __restrict__ partials) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ __align__(8) uint64_t full[MG_NST];
-  __shared__ double tab[128];
+  __shared__ float tab[27 * 128];  // omega / a_P by [z class][y class][x class][code & 127]
   __shared__ double red[32 * 3];
   if (S->done) return;
   unsigned char* raw = dyn;
@@ -309,12 +308,16 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
     mbar_fence_init();
   }
   const bool flat = D.nzg == 1;  // 2D grid: no z faces anywhere
-  if (tid < 128) tab[tid] = 1.0 / diag_of(C, (unsigned)tid, false, false, false, false, flat, flat);
+  for (int e = tid; e < 27 * 128; e += NTHR) {
+    const int cls = e >> 7, cx = cls % 3, cy = (cls / 3) % 3, cz = cls / 9;
+    tab[e] = (float)(M.omega / diag_of(C, (unsigned)(e & 127), cx == 1, cx == 2, cy == 1, cy == 2, flat || cz == 1,
+                                       flat || cz == 2));
+  }
   uint32_t seq = 0;
   double acc[3] = {0, 0, 0};
   const long plane = (long)D.nx * D.ny;
   const int coff = (ly + 1) * BOXW + lx + 2;
-  const double om = M.omega, om1 = 1.0 - M.omega;
+  const double om1 = 1.0 - M.omega;
   const double sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0], sy1 = C.same[1][1];
   const double sz0 = C.same[2][0], sz1 = C.same[2][1];
   const double dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
@@ -326,8 +329,11 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
     const int gx = xo + lx, gy = yo + ly;
     const bool colv = gx < D.nx;
     const bool row0 = colv && gy < D.ny, row1 = colv && gy + 1 < D.ny;
-    // my 2x2 block touches the domain surface in x or y?
-    const bool edge_xy = gx == 0 || gx + 1 == D.nx - 1 || gy == 0 || gy + 1 >= D.ny - 1;
+    // xy classes of my four cells a,b,c,d (4 bits each)
+    unsigned ocls = (unsigned)(3 * mg_cls(gy, D.ny) + mg_cls(gx, D.nx)) | (unsigned)(3 * mg_cls(gy, D.ny) + mg_cls(gx + 1, D.nx)) << 4 |
+                    (unsigned)(3 * mg_cls(gy + 1, D.ny) + mg_cls(gx, D.nx)) << 8 |
+                    (unsigned)(3 * mg_cls(gy + 1, D.ny) + mg_cls(gx + 1, D.nx)) << 12;
+    asm volatile("" : "+r"(ocls));
 
     __syncthreads();  // rings idle, barriers + table initialised
     int issued = 0;
@@ -343,13 +349,15 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
     const int tr = tid / 14, tc = tid - tr * 14;
     const int sy = yo - 1 + tr, sx = xo - 2 + tc;
     const bool rowok = tid < 252 && sy >= 0 && sy < D.ny;
-    unsigned vmask = 0, smask = 0;
+    unsigned vmask = 0, scls = 0;  // valid bits; 4-bit xy class (3*ycls + xcls) of each of my 5 cells
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       const int x = sx + 14 * i;
       if (rowok && tc + 14 * i < BOXW && x >= 0 && x < D.nx) vmask |= 1u << i;
-      if (sy == 0 || sy == D.ny - 1 || x == 0 || x == D.nx - 1) smask |= 1u << i;
+      scls |= (unsigned)(3 * mg_cls(sy, D.ny) + mg_cls(x, D.nx)) << (4 * i);
     }
+    // keep them packed (the compiler would otherwise re-derive every bit from coordinates per use)
+    asm volatile("" : "+r"(vmask), "+r"(scls));
     const long cbase = (long)sy * D.nx + sx;
     const long ebase = POST ? (long)(M.fy ? sy >> 1 : sy) * M.nx1 + (sx >> 1) : 0;
     const int ubase = tr * BOXW + tc;
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
       const float* ep = POST ? M.e1 + (long)(M.fz ? lz >> 1 : lz) * M.ny1 * M.nx1 + ebase : nullptr;
 #pragma unroll
       for (int i = 0; i < 5; i++)
-        if (vmask >> i & 1u) {
+        if (vmask & (1u << i)) {
           pc[i] = cp[14 * i];
           if (POST) pe[i] = ep[7 * i];
         }
@@ -375,22 +383,23 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
       double* dst = U + (j & (MG_NU - 1)) * MG_UPLANE + ubase;
       const int lz = zb - 1 + j;
       const bool zin = lz >= 0 && lz < D.nz;
-      const bool zsurf = !flat && (D.z0 + lz == 0 || D.z0 + lz == D.nzg - 1);
+      const float* tz = tab + 9 * 128 * mg_cls(D.z0 + lz, D.nzg);
+      unsigned live = zin ? vmask : 0u;
+      asm volatile("" : "+r"(live));
       double u[5];
 #pragma unroll
       for (int i = 0; i < 5; i++) {
         u[i] = 0.0;
-        if (zin && (vmask >> i & 1u)) {
-          const double di = (zsurf || (smask >> i & 1u)) ? mg_dinv_exact(C, D, pc[i], sx + 14 * i, sy, lz) : tab[pc[i] & 127u];
-          u[i] = om * src[14 * i] * di;
+        if (live & (1u << i)) {
+          u[i] = src[14 * i] * (double)tz[(((scls >> (4 * i)) & 15u) << 7) | (pc[i] & 127u)];
           if (POST) u[i] += (double)pe[i];
         }
       }
       if (j + 1 < nplanes) prefetch(j + 1);
       if (tid < 252) {
 #pragma unroll
-        for (int i = 0; i < 5; i++)
-          if (tc + 14 * i < BOXW) dst[14 * i] = u[i];
+        for (int i = 0; i < 4; i++) dst[14 * i] = u[i];
+        if (tc < BOXW - 56) dst[56] = u[4];
       }
     };
     prefetch(0);
@@ -496,25 +505,16 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
           M.b1[((long)lz * M.ny1 + (M.fy ? gy >> 1 : gy)) * M.nx1 + (gx >> 1)] = s;
         }
       } else {
-        double da, db, dc, dd;
-        if (edge_xy || (!flat && (D.z0 + lz == 0 || D.z0 + lz == D.nzg - 1))) {
-          da = row0 ? mg_dinv_exact(C, D, ca, gx, gy, lz) : 0.0;
-          db = row0 ? mg_dinv_exact(C, D, cb, gx + 1, gy, lz) : 0.0;
-          dc = row1 ? mg_dinv_exact(C, D, cc, gx, gy + 1, lz) : 0.0;
-          dd = row1 ? mg_dinv_exact(C, D, cd, gx + 1, gy + 1, lz) : 0.0;
-        } else {
-          da = tab[ca & 127u];
-          db = tab[cb & 127u];
-          dc = tab[cc & 127u];
-          dd = tab[cd & 127u];
-        }
+        const float* tz = tab + 9 * 128 * mg_cls(D.z0 + lz, D.nzg);
+        const double da = tz[(ocls & 0xf) << 7 | (ca & 127u)], db = tz[(ocls >> 4 & 0xf) << 7 | (cb & 127u)];
+        const double dc = tz[(ocls >> 8 & 0xf) << 7 | (cc & 127u)], dd = tz[(ocls >> 12 & 0xf) << 7 | (cd & 127u)];
         if (row0) {
-          const double za = om1 * pt.x + om * da * (r0.x + qa), zb2 = om1 * pt.y + om * db * (r0.y + qb);
+          const double za = om1 * pt.x + da * (r0.x + qa), zb2 = om1 * pt.y + db * (r0.y + qb);
           *reinterpret_cast<double2*>(zout + ci) = make_double2(za, zb2);
           acc[0] += r0.x * za + r0.y * zb2;
         }
         if (row1) {
-          const double zc2 = om1 * pb.x + om * dc * (r1.x + qc), zd = om1 * pb.y + om * dd * (r1.y + qd);
+          const double zc2 = om1 * pb.x + dc * (r1.x + qc), zd = om1 * pb.y + dd * (r1.y + qd);
           *reinterpret_cast<double2*>(zout + ci + D.nx) = make_double2(zc2, zd);
           acc[0] += r1.x * zc2 + r1.y * zd;
         }
