@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,11 +50,14 @@ struct Ctx {
   // grid-solver workspace (grow-only)
   size_t cap_field = 0;  // doubles per field incl. halo planes
   double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr;
-  double* z = nullptr;   // preconditioned residual of the multigrid path (no halo planes)
+  float* z = nullptr;    // preconditioned residual of the multigrid path (FP32, no halo planes)
   size_t cap_z = 0;
+  float* u = nullptr;    // omega r / a_P (FP32, pitched rows, one halo plane below and above)
+  size_t cap_u = 0;
   float* mg_pool = nullptr;  // stored multigrid levels (grow-only)
   size_t cap_mg = 0;         // floats
   double* mg_inv = nullptr;  // dense inverse of the coarsest level
+  float* mg_tab = nullptr;   // omega/d and d(1-omega)/omega by (position class, code byte)
   uint8_t *code = nullptr, *mask = nullptr;
   size_t cap_aux = 0;  // doubles in qL/qR
   double *qL = nullptr, *qR = nullptr;
@@ -99,7 +103,16 @@ inline int fail(int code, const char* fmt, ...) {
     if (rc_ != 0) return rc_; \
   } while (0)
 
-#define KB_LAUNCHED() (kb::ctx().launches++)
+// KEFFB200_DEBUG_SYNC=1: synchronise after every launch and name the first one that faults
+inline void debug_sync(const char* file, int line) {
+  static const bool on = getenv("KEFFB200_DEBUG_SYNC") != nullptr;
+  if (!on) return;
+  cudaError_t e = cudaStreamSynchronize(ctx().st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) fprintf(stderr, "keffb200: launch before %s:%d failed: %s\n", file, line, cudaGetErrorString(e));
+}
+
+#define KB_LAUNCHED() (kb::ctx().launches++, kb::debug_sync(__FILE__, __LINE__))
 
 constexpr int PARTIAL_SLOTS = 1 << 15;  // per-CTA partial sums, 3 doubles each
 

@@ -266,61 +266,79 @@ __global__ void __launch_bounds__(MG_DENSE_MAX) k_mg_dense_apply(const double* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// voxel-grid (level 0) passes.  Same tiling as k_stencil_tma: a CTA marches a 64x16 xy tile in z, raw
-// planes of r arrive by TMA in a ring; every arrived plane is turned once into u = omega r / a_P
-// (POST: + the prolongated coarse correction) over the whole staged box -- halo included, zero outside
-// the domain -- and kept in a second ring of 4 planes; the stencil then needs no boundary logic at
-// all (a face towards the outside multiplies a zero).  1/a_P comes from a 128-entry table indexed by
-// the code byte (interior cells) or is evaluated exactly (cells on the domain surface).
-//   PRE : b1[aggregate] = sum over its cells of (1-omega) r_P + sum_f c_f u_nb        (FP32 out)
-//   POST: z_P = (1-omega) v_P + omega/a_P (r_P + sum_f c_f v_nb),  partial r.z        (FP64 out)
+// voxel-grid (level 0) passes.  The whole preconditioner works in FP32: the CG update kernel leaves
+//     u = omega r / a_P     (FP32, pitched rows, one halo plane below and above)
+// next to the FP64 residual, and the two passes below are plain 7-point stencils on u with the same
+// tiling as k_stencil_tma (a CTA marches a 64x16 xy tile in z; planes of u arrive by TMA in a
+// shared-memory ring, zero-filled outside the domain, so a face towards the outside multiplies a
+// zero and needs no boundary logic).  With d = a_P rounded to FP32 (table indexed by position class
+// and code byte; r_P is recovered as d u_P / omega, i.e. the cycle is the exact V-cycle of the
+// operator whose diagonal is d -- symmetric, as CG needs):
+//   PRE : b1[aggregate] = sum over its cells of ((1-omega)/omega) d_P u_P + sum_f c_f u_nb
+//   POST: v = u + P e1;  z_P = (1-omega) v_P + u_P + (omega/d_P) sum_f c_f v_nb;  partial r.z
+// P e1 is never materialised: a 2x2 cell block of a thread is one aggregate in xy, so the thread adds
+// its own aggregate's correction and those of the four in-plane neighbour aggregates (and of the
+// aggregate below/above) to the staged neighbour values on the fly.
 // ------------------------------------------------------------------------------------------------
-constexpr int MG_NST = 4, MG_NU = 4, MG_UPLANE = BOXW * BOXH;
-constexpr int MG_SMEM = MG_NST * STAGE_STRIDE + MG_NU * MG_UPLANE * 8;
+// the staged box starts 4 cells left of the tile: a TMA box must start on a 16-byte boundary of the row
+constexpr int MG_NST = 6, MG_BOXW = TX + 8, MG_HX = 4;
+constexpr int MG_STAGE_BYTES = MG_BOXW * BOXH * 4;
+constexpr int MG_STAGE_STRIDE = (MG_STAGE_BYTES + 127) / 128 * 128;
 
 struct MgFine {
   const float* e1;  // level-1 correction (POST)
   float* b1;        // level-1 right-hand side (PRE)
-  int nx1, ny1;
-  int fy, fz;       // y / z coarsened (x always is: nx even >= 2)
-  double omega;
+  int nx1, ny1, nz1;
+  int fy, fz;       // y / z coarsened (x always is: nx even >= 4)
+  float omega;
 };
 
 // position class of a cell along one axis: 0 interior, 1 first, 2 last
-__device__ __forceinline__ int mg_cls(int i, int n) { return i == 0 ? 1 : (i == n - 1 ? 2 : 0); }
+__host__ __device__ __forceinline__ int mg_cls(int i, int n) { return i == 0 ? 1 : (i == n - 1 ? 2 : 0); }
+
+// a_P of a cell of position class cls = xcls + 3 ycls + 9 zcls with code byte c, rounded to FP32
+__device__ __forceinline__ float mg_diag32(const Coef& C, int cls, unsigned c, bool flat) {
+  const int cx = cls % 3, cy = (cls / 3) % 3, cz = cls / 9;
+  return (float)diag_of(C, c, cx == 1, cx == 2, cy == 1, cy == 2, flat || cz == 1, flat || cz == 2);
+}
+
+__device__ __forceinline__ float pickf(bool c, float a, float b) { return c ? a : b; }
+
+// the three per-solve tables over (position class, code byte): [0] omega/d, [1] d (1-omega)/omega
+constexpr int MG_TAB = 27 * 128;
+__global__ void k_mg_tables(float* __restrict__ t, const Coef C, int flat, float omega) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= MG_TAB) return;
+  const float d = mg_diag32(C, e >> 7, (unsigned)(e & 127), flat != 0);
+  t[e] = omega / d;
+  t[MG_TAB + e] = d * ((1.f - omega) / omega);
+}
 
 template <int POST>
-__global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUtensorMap tm,
-                                                     const double* __restrict__ r, const uint8_t* __restrict__ code,
-                                                     double* __restrict__ zout, const MgFine M, const Coef C,
-                                                     const Dom D, const Plan P, const Scal* __restrict__ S,
-                                                     double* __restrict__ partials) {
-  extern __shared__ __align__(128) unsigned char dyn[];
+__global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUtensorMap tm,
+                                                     const uint8_t* __restrict__ code, const float* __restrict__ gtab,
+                                                     float* __restrict__ zout,
+                                                     const MgFine M, const Coef C, const Dom D, const Plan P,
+                                                     const Scal* __restrict__ S, double* __restrict__ partials) {
+  __shared__ __align__(128) unsigned char tiles[MG_NST * MG_STAGE_STRIDE];
   __shared__ __align__(8) uint64_t full[MG_NST];
-  __shared__ float tab[27 * 128];  // omega / a_P by [z class][y class][x class][code & 127]
+  __shared__ float tab[27 * 128];  // PRE: d (1-omega)/omega   POST: omega / d
   __shared__ double red[32 * 3];
   if (S->done) return;
-  unsigned char* raw = dyn;
-  double* U = reinterpret_cast<double*>(dyn + MG_NST * STAGE_STRIDE);
   const int tid = threadIdx.x, lx = (tid & 31) * 2, ly = (tid >> 5) * 2;
   if (tid == 0) {
     for (int s = 0; s < MG_NST; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
-  const bool flat = D.nzg == 1;  // 2D grid: no z faces anywhere
-  for (int e = tid; e < 27 * 128; e += NTHR) {
-    const int cls = e >> 7, cx = cls % 3, cy = (cls / 3) % 3, cz = cls / 9;
-    tab[e] = (float)(M.omega / diag_of(C, (unsigned)(e & 127), cx == 1, cx == 2, cy == 1, cy == 2, flat || cz == 1,
-                                       flat || cz == 2));
-  }
+  const float om1 = 1.f - M.omega;
+  for (int e = tid; e < MG_TAB; e += NTHR) tab[e] = gtab[(POST ? 0 : MG_TAB) + e];
   uint32_t seq = 0;
   double acc[3] = {0, 0, 0};
   const long plane = (long)D.nx * D.ny;
-  const int coff = (ly + 1) * BOXW + lx + 2;
-  const double om1 = 1.0 - M.omega;
-  const double sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0], sy1 = C.same[1][1];
-  const double sz0 = C.same[2][0], sz1 = C.same[2][1];
-  const double dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
+  const int coff = (ly + 1) * MG_BOXW + lx + MG_HX;
+  const float sx0 = (float)C.same[0][0], sx1 = (float)C.same[0][1], sy0 = (float)C.same[1][0];
+  const float sy1 = (float)C.same[1][1], sz0 = (float)C.same[2][0], sz1 = (float)C.same[2][1];
+  const float dfx = (float)C.diff[0], dfy = (float)C.diff[1], dfz = (float)C.diff[2];
 
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
@@ -329,196 +347,177 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
     const int gx = xo + lx, gy = yo + ly;
     const bool colv = gx < D.nx;
     const bool row0 = colv && gy < D.ny, row1 = colv && gy + 1 < D.ny;
-    // xy classes of my four cells a,b,c,d (4 bits each)
-    unsigned ocls = (unsigned)(3 * mg_cls(gy, D.ny) + mg_cls(gx, D.nx)) | (unsigned)(3 * mg_cls(gy, D.ny) + mg_cls(gx + 1, D.nx)) << 4 |
-                    (unsigned)(3 * mg_cls(gy + 1, D.ny) + mg_cls(gx, D.nx)) << 8 |
-                    (unsigned)(3 * mg_cls(gy + 1, D.ny) + mg_cls(gx + 1, D.nx)) << 12;
-    asm volatile("" : "+r"(ocls));
+    // xy position classes of my four cells a,b (row gy) and c,d (row gy+1), pre-shifted table offsets
+    const int ya = 3 * mg_cls(gy, D.ny), yc = 3 * mg_cls(gy + 1, D.ny);
+    const int xa = mg_cls(gx, D.nx), xb = mg_cls(gx + 1, D.nx);
+    const int ta = (ya + xa) << 7, tb = (ya + xb) << 7, tc = (yc + xa) << 7, td = (yc + xb) << 7;
+    // aggregate of my block and its in-plane neighbours (POST)
+    const int X = gx >> 1, Y = M.fy ? gy >> 1 : gy;
+    const bool hW = POST && row0 && X > 0, hE = POST && row0 && X + 1 < M.nx1;
+    const bool hN = POST && row0 && Y > 0, hS = POST && row0 && Y + 1 < M.ny1;
+    const long eoff = (long)Y * M.nx1 + X;
+    const long eplane = (long)M.nx1 * M.ny1;
 
-    __syncthreads();  // rings idle, barriers + table initialised
-    int issued = 0;
+    __syncthreads();  // ring idle (previous item consumed; barriers and table initialised)
     if (tid == 0) {
-      for (; issued < min(MG_NST, nplanes); issued++) {
-        const uint32_t st = (seq + issued) % MG_NST;
-        mbar_expect_tx(&full[st], STAGE_BYTES);
-        tma_load_3d(raw + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + issued);
+      const int npre = min(MG_NST, nplanes);
+      for (int k = 0; k < npre; k++) {
+        const uint32_t st = (seq + k) % MG_NST;
+        mbar_expect_tx(&full[st], MG_STAGE_BYTES);
+        tma_load_3d(tiles + st * MG_STAGE_STRIDE, &tm, &full[st], xo - MG_HX, yo - 1, zb + k);
       }
     }
-    // Staging assignment: thread t owns row t/14 of the 68x18 box and the cells tc, tc+14, .. tc+56 of
-    // it (tc = t%14), so every global address is one base register plus an immediate.
-    const int tr = tid / 14, tc = tid - tr * 14;
-    const int sy = yo - 1 + tr, sx = xo - 2 + tc;
-    const bool rowok = tid < 252 && sy >= 0 && sy < D.ny;
-    unsigned vmask = 0, scls = 0;  // valid bits; 4-bit xy class (3*ycls + xcls) of each of my 5 cells
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-      const int x = sx + 14 * i;
-      if (rowok && tc + 14 * i < BOXW && x >= 0 && x < D.nx) vmask |= 1u << i;
-      scls |= (unsigned)(3 * mg_cls(sy, D.ny) + mg_cls(x, D.nx)) << (4 * i);
-    }
-    // keep them packed (the compiler would otherwise re-derive every bit from coordinates per use)
-    asm volatile("" : "+r"(vmask), "+r"(scls));
-    const long cbase = (long)sy * D.nx + sx;
-    const long ebase = POST ? (long)(M.fy ? sy >> 1 : sy) * M.nx1 + (sx >> 1) : 0;
-    const int ubase = tr * BOXW + tc;
-    unsigned pc[5];  // code bytes of the plane staged next, fetched one step ahead
-    float pe[5];     // (POST) level-1 corrections of the same cells
-    auto prefetch = [&](int j) {
-      const int lz = zb - 1 + j;
-      if (lz < 0 || lz >= D.nz) return;
-      const uint8_t* cp = code + (long)lz * plane + cbase;
-      const float* ep = POST ? M.e1 + (long)(M.fz ? lz >> 1 : lz) * M.ny1 * M.nx1 + ebase : nullptr;
-#pragma unroll
-      for (int i = 0; i < 5; i++)
-        if (vmask & (1u << i)) {
-          pc[i] = cp[14 * i];
-          if (POST) pe[i] = ep[7 * i];
-        }
-    };
-    // plane j of the item (local plane zb-1+j)  ->  U ring slot j & 3
-    auto transform = [&](int j) {
-      const uint32_t sq = seq + j, st = sq % MG_NST;
-      mbar_wait(&full[st], (sq / MG_NST) & 1);
-      const double* src = reinterpret_cast<const double*>(raw + st * STAGE_STRIDE) + ubase;
-      double* dst = U + (j & (MG_NU - 1)) * MG_UPLANE + ubase;
-      const int lz = zb - 1 + j;
-      const bool zin = lz >= 0 && lz < D.nz;
-      const float* tz = tab + 9 * 128 * mg_cls(D.z0 + lz, D.nzg);
-      unsigned live = zin ? vmask : 0u;
-      asm volatile("" : "+r"(live));
-      double u[5];
-#pragma unroll
-      for (int i = 0; i < 5; i++) {
-        u[i] = 0.0;
-        if (live & (1u << i)) {
-          u[i] = src[14 * i] * (double)tz[(((scls >> (4 * i)) & 15u) << 7) | (pc[i] & 127u)];
-          if (POST) u[i] += (double)pe[i];
-        }
-      }
-      if (j + 1 < nplanes) prefetch(j + 1);
-      if (tid < 252) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) dst[14 * i] = u[i];
-        if (tc < BOXW - 56) dst[56] = u[4];
-      }
-    };
-    prefetch(0);
-    transform(0);
-    transform(1);
-    if (nplanes > 2) transform(2);
-
     long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of cell a in plane zb
     unsigned cn0 = row0 ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
     unsigned cn1 = row1 ? *reinterpret_cast<const unsigned short*>(code + ci + D.nx) : 0u;
-    double2 rn0 = row0 ? *reinterpret_cast<const double2*>(r + ci) : make_double2(0, 0);
-    double2 rn1 = row1 ? *reinterpret_cast<const double2*>(r + ci + D.nx) : make_double2(0, 0);
-    // conductances of the faces towards the plane below (zero-valued neighbour when there is none)
-    double fa, fb, fc, fd;
+    // corrections of my aggregate column: E[0] own, E[1..4] W,E,N,S neighbours; Ez of the pair below / above
+    float E0 = 0.f, EW = 0.f, EE = 0.f, EN = 0.f, ES = 0.f, Eprev = 0.f, Enext = 0.f;
+    float nE0 = 0.f, nEW = 0.f, nEE = 0.f, nEN = 0.f, nES = 0.f;  // prefetched for the next aggregate plane
+    auto load_E = [&](int Z, float& a0, float& aw, float& ae, float& an, float& as) {
+      a0 = aw = ae = an = as = 0.f;
+      if (Z < 0 || Z >= M.nz1) return;
+      const float* ep = M.e1 + (long)Z * eplane + eoff;
+      if (row0) a0 = ep[0];
+      if (hW) aw = ep[-1];
+      if (hE) ae = ep[1];
+      if (hN) an = ep[-M.nx1];
+      if (hS) as = ep[M.nx1];
+    };
+    if (POST) {
+      const int Z = M.fz ? zb >> 1 : zb;
+      float d1, d2, d3, d4;
+      load_E(Z - 1, Eprev, d1, d2, d3, d4);
+      load_E(Z, nE0, nEW, nEE, nEN, nES);
+    }
+    float2 pt, pb, lt, lb;  // current plane (top row a,b / bottom row c,d) and the plane below
+    float fa, fb, fc, fd;   // conductances of the faces towards the plane below
     {
+      const uint32_t q0 = seq % MG_NST, q1 = (seq + 1) % MG_NST;
+      mbar_wait(&full[q0], (seq / MG_NST) & 1);
+      const float* lo = reinterpret_cast<const float*>(tiles + q0 * MG_STAGE_STRIDE) + coff;
+      lt = *reinterpret_cast<const float2*>(lo);
+      lb = *reinterpret_cast<const float2*>(lo + MG_BOXW);
+      mbar_wait(&full[q1], ((seq + 1) / MG_NST) & 1);
+      const float* c0 = reinterpret_cast<const float*>(tiles + q1 * MG_STAGE_STRIDE) + coff;
+      pt = *reinterpret_cast<const float2*>(c0);
+      pb = *reinterpret_cast<const float2*>(c0 + MG_BOXW);
       const unsigned ca = cn0 & 0xffu, cb = cn0 >> 8, cc = cn1 & 0xffu, cd = cn1 >> 8;
-      fa = pick(ca & C_F, dfz, pick(ca & C_PH, sz1, sz0));
-      fb = pick(cb & C_F, dfz, pick(cb & C_PH, sz1, sz0));
-      fc = pick(cc & C_F, dfz, pick(cc & C_PH, sz1, sz0));
-      fd = pick(cd & C_F, dfz, pick(cd & C_PH, sz1, sz0));
+      fa = pickf(ca & C_F, dfz, pickf(ca & C_PH, sz1, sz0));
+      fb = pickf(cb & C_F, dfz, pickf(cb & C_PH, sz1, sz0));
+      fc = pickf(cc & C_F, dfz, pickf(cc & C_PH, sz1, sz0));
+      fd = pickf(cd & C_F, dfz, pickf(cd & C_PH, sz1, sz0));
     }
     float sacc = 0.f;
 
     for (int k = 1; k <= len; k++) {
       const int lz = zb + k - 1;
-      __syncthreads();  // plane k+1 of the U ring is visible; raw stages of planes <= k+1 are consumed
-      if (tid == 0) {
-        for (; issued < nplanes && issued <= k + 1 + MG_NST; issued++) {
-          // stage of plane `issued` was last used by plane issued-MG_NST <= k+1: consumed
-          const uint32_t st = (seq + issued) % MG_NST;
-          mbar_expect_tx(&full[st], STAGE_BYTES);
-          tma_load_3d(raw + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + issued);
-        }
+      __syncthreads();  // every thread is done with plane k-1's stage
+      if (tid == 0 && k - 1 + MG_NST < nplanes) {
+        const uint32_t st = (seq + k - 1) % MG_NST;
+        mbar_expect_tx(&full[st], MG_STAGE_BYTES);
+        tma_load_3d(tiles + st * MG_STAGE_STRIDE, &tm, &full[st], xo - MG_HX, yo - 1, zb + k - 1 + MG_NST);
       }
+      const uint32_t sc = (seq + k) % MG_NST, sn = (seq + k + 1) % MG_NST;
+      mbar_wait(&full[sn], ((seq + k + 1) / MG_NST) & 1);
+      const float* cur = reinterpret_cast<const float*>(tiles + sc * MG_STAGE_STRIDE) + coff;
+      const float* nxt = reinterpret_cast<const float*>(tiles + sn * MG_STAGE_STRIDE) + coff;
+      const float2 nt0 = *reinterpret_cast<const float2*>(nxt), nb0 = *reinterpret_cast<const float2*>(nxt + MG_BOXW);
+      float2 ut = nt0, ub = nb0;
       const unsigned k0 = cn0, k1 = cn1;
-      const double2 r0 = rn0, r1 = rn1;
-      if (k < len) {  // prefetch my codes and residuals of the next plane
-        if (row0) {
-          cn0 = *reinterpret_cast<const unsigned short*>(code + ci + plane);
-          rn0 = *reinterpret_cast<const double2*>(r + ci + plane);
-        }
-        if (row1) {
-          cn1 = *reinterpret_cast<const unsigned short*>(code + ci + plane + D.nx);
-          rn1 = *reinterpret_cast<const double2*>(r + ci + plane + D.nx);
-        }
+      if (k < len) {
+        if (row0) cn0 = *reinterpret_cast<const unsigned short*>(code + ci + plane);
+        if (row1) cn1 = *reinterpret_cast<const unsigned short*>(code + ci + plane + D.nx);
       }
-      if (k + 2 < nplanes) transform(k + 2);
-
-      const double* cur = U + (k & (MG_NU - 1)) * MG_UPLANE + coff;
-      const double* blw = U + ((k - 1) & (MG_NU - 1)) * MG_UPLANE + coff;
-      const double* abv = U + ((k + 1) & (MG_NU - 1)) * MG_UPLANE + coff;
-      const double2 pt = *reinterpret_cast<const double2*>(cur), pb = *reinterpret_cast<const double2*>(cur + BOXW);
-      const double2 pn = *reinterpret_cast<const double2*>(cur - BOXW);
-      const double2 ps = *reinterpret_cast<const double2*>(cur + 2 * BOXW);
-      const double pwt = cur[-1], pet = cur[2], pwb = cur[BOXW - 1], peb = cur[BOXW + 2];
-      const double2 lt = *reinterpret_cast<const double2*>(blw), lb = *reinterpret_cast<const double2*>(blw + BOXW);
-      const double2 ut = *reinterpret_cast<const double2*>(abv), ub = *reinterpret_cast<const double2*>(abv + BOXW);
+      float2 pn = *reinterpret_cast<const float2*>(cur - MG_BOXW);
+      float2 ps = *reinterpret_cast<const float2*>(cur + 2 * MG_BOXW);
+      float pwt = cur[-1], pet = cur[2], pwb = cur[MG_BOXW - 1], peb = cur[MG_BOXW + 2];
+      const float2 ct = pt, cb2 = pb;  // u of my own cells (before the correction is added)
+      float2 bt = lt, bb = lb;         // plane below
+      float e0 = 0.f;
+      if (POST) {
+        // corrections: a new aggregate plane starts at every plane (z not coarsened) or at even planes
+        const bool first_of_pair = !M.fz || !(lz & 1);
+        if (first_of_pair) {
+          if (k > 1) Eprev = E0;
+          E0 = nE0; EW = nEW; EE = nEE; EN = nEN; ES = nES;
+          load_E((M.fz ? lz >> 1 : lz) + 1, nE0, nEW, nEE, nEN, nES);
+        }
+        const bool has_lo = D.z0 + lz > 0, has_hi = D.z0 + lz < D.nzg - 1;
+        const float Eb = !has_lo ? 0.f : ((M.fz && (lz & 1)) ? E0 : Eprev);
+        const float Ea = !has_hi ? 0.f : ((M.fz && !(lz & 1) && lz + 1 < D.nz) ? E0 : nE0);
+        e0 = E0;
+        const float e0c = row1 ? E0 : 0.f;
+        pt.x += e0; pt.y += e0; pb.x += e0c; pb.y += e0c;
+        pwt += EW; pwb += EW; pet += EE; peb += EE;
+        pn.x += EN; pn.y += EN; ps.x += ES; ps.y += ES;
+        bt.x += Eb; bt.y += Eb; bb.x += Eb; bb.y += Eb;
+        ut.x += Ea; ut.y += Ea; ub.x += Ea; ub.y += Ea;
+      }
       const unsigned ca = k0 & 0xffu, cb = k0 >> 8, cc = k1 & 0xffu, cd = k1 >> 8;
       const bool ha = ca & C_PH, hb = cb & C_PH, hc = cc & C_PH, hd = cd & C_PH;
-      double g;
-      // from the plane below, then towards the plane above (kept for the next step)
-      double qa = fa * lt.x, qb = fb * lt.y, qc = fc * lb.x, qd = fd * lb.y;
-      fa = pick(ca & C_B, dfz, pick(ha, sz1, sz0));
-      fb = pick(cb & C_B, dfz, pick(hb, sz1, sz0));
-      fc = pick(cc & C_B, dfz, pick(hc, sz1, sz0));
-      fd = pick(cd & C_B, dfz, pick(hd, sz1, sz0));
+      float g;
+      // plane below, then the plane above (its conductances are kept for the next step)
+      float qa = fa * bt.x, qb = fb * bt.y, qc = fc * bb.x, qd = fd * bb.y;
+      fa = pickf(ca & C_B, dfz, pickf(ha, sz1, sz0));
+      fb = pickf(cb & C_B, dfz, pickf(hb, sz1, sz0));
+      fc = pickf(cc & C_B, dfz, pickf(hc, sz1, sz0));
+      fd = pickf(cd & C_B, dfz, pickf(hd, sz1, sz0));
       qa += fa * ut.x;
       qb += fb * ut.y;
       qc += fc * ub.x;
       qd += fd * ub.y;
       // x faces
-      qa += pick(ca & C_W, dfx, pick(ha, sx1, sx0)) * pwt;
-      g = pick(ca & C_E, dfx, pick(ha, sx1, sx0));
+      qa += pickf(ca & C_W, dfx, pickf(ha, sx1, sx0)) * pwt;
+      g = pickf(ca & C_E, dfx, pickf(ha, sx1, sx0));
       qa += g * pt.y;
       qb += g * pt.x;
-      qb += pick(cb & C_E, dfx, pick(hb, sx1, sx0)) * pet;
-      qc += pick(cc & C_W, dfx, pick(hc, sx1, sx0)) * pwb;
-      g = pick(cc & C_E, dfx, pick(hc, sx1, sx0));
+      qb += pickf(cb & C_E, dfx, pickf(hb, sx1, sx0)) * pet;
+      qc += pickf(cc & C_W, dfx, pickf(hc, sx1, sx0)) * pwb;
+      g = pickf(cc & C_E, dfx, pickf(hc, sx1, sx0));
       qc += g * pb.y;
       qd += g * pb.x;
-      qd += pick(cd & C_E, dfx, pick(hd, sx1, sx0)) * peb;
+      qd += pickf(cd & C_E, dfx, pickf(hd, sx1, sx0)) * peb;
       // y faces
-      qa += pick(ca & C_N, dfy, pick(ha, sy1, sy0)) * pn.x;
-      g = pick(ca & C_S, dfy, pick(ha, sy1, sy0));
+      qa += pickf(ca & C_N, dfy, pickf(ha, sy1, sy0)) * pn.x;
+      g = pickf(ca & C_S, dfy, pickf(ha, sy1, sy0));
       qa += g * pb.x;
       qc += g * pt.x;
-      qc += pick(cc & C_S, dfy, pick(hc, sy1, sy0)) * ps.x;
-      qb += pick(cb & C_N, dfy, pick(hb, sy1, sy0)) * pn.y;
-      g = pick(cb & C_S, dfy, pick(hb, sy1, sy0));
+      qc += pickf(cc & C_S, dfy, pickf(hc, sy1, sy0)) * ps.x;
+      qb += pickf(cb & C_N, dfy, pickf(hb, sy1, sy0)) * pn.y;
+      g = pickf(cb & C_S, dfy, pickf(hb, sy1, sy0));
       qb += g * pb.y;
       qd += g * pt.y;
-      qd += pick(cd & C_S, dfy, pick(hd, sy1, sy0)) * ps.y;
+      qd += pickf(cd & C_S, dfy, pickf(hd, sy1, sy0)) * ps.y;
 
+      const float* tz = tab + 9 * 128 * mg_cls(D.z0 + lz, D.nzg);
+      const float wa = tz[ta | (ca & 127u)], wb = tz[tb | (cb & 127u)], wc = tz[tc | (cc & 127u)], wd = tz[td | (cd & 127u)];
       if (!POST) {
         float s = 0.f;
-        if (row0) s += (float)((om1 * r0.x + qa) + (om1 * r0.y + qb));
-        if (row1) s += (float)((om1 * r1.x + qc) + (om1 * r1.y + qd));
+        if (row0) s += (wa * ct.x + qa) + (wb * ct.y + qb);
+        if (row1) s += (wc * cb2.x + qc) + (wd * cb2.y + qd);
         if (M.fz) {
           sacc = (lz & 1) ? sacc + s : s;
-          if (row0 && ((lz & 1) || lz == D.nz - 1))
-            M.b1[((long)(lz >> 1) * M.ny1 + (M.fy ? gy >> 1 : gy)) * M.nx1 + (gx >> 1)] = sacc;
+          if (row0 && ((lz & 1) || lz == D.nz - 1)) M.b1[(long)(lz >> 1) * ((long)M.nx1 * M.ny1) + (long)Y * M.nx1 + X] = sacc;
         } else if (row0) {
-          M.b1[((long)lz * M.ny1 + (M.fy ? gy >> 1 : gy)) * M.nx1 + (gx >> 1)] = s;
+          M.b1[(long)lz * ((long)M.nx1 * M.ny1) + (long)Y * M.nx1 + X] = s;
         }
       } else {
-        const float* tz = tab + 9 * 128 * mg_cls(D.z0 + lz, D.nzg);
-        const double da = tz[(ocls & 0xf) << 7 | (ca & 127u)], db = tz[(ocls >> 4 & 0xf) << 7 | (cb & 127u)];
-        const double dc = tz[(ocls >> 8 & 0xf) << 7 | (cc & 127u)], dd = tz[(ocls >> 12 & 0xf) << 7 | (cd & 127u)];
+        // z = (1-omega) v_P + u_P + (omega/d) sum;  r_P = d u_P / omega
         if (row0) {
-          const double za = om1 * pt.x + da * (r0.x + qa), zb2 = om1 * pt.y + db * (r0.y + qb);
-          *reinterpret_cast<double2*>(zout + ci) = make_double2(za, zb2);
-          acc[0] += r0.x * za + r0.y * zb2;
+          const float za = om1 * pt.x + ct.x + wa * qa, zb2 = om1 * pt.y + ct.y + wb * qb;
+          *reinterpret_cast<float2*>(zout + ci) = make_float2(za, zb2);
+          acc[0] += (double)(__fdividef(ct.x, wa) * za) + (double)(__fdividef(ct.y, wb) * zb2);
         }
         if (row1) {
-          const double zc2 = om1 * pb.x + dc * (r1.x + qc), zd = om1 * pb.y + dd * (r1.y + qd);
-          *reinterpret_cast<double2*>(zout + ci + D.nx) = make_double2(zc2, zd);
-          acc[0] += r1.x * zc2 + r1.y * zd;
+          const float zc2 = om1 * pb.x + cb2.x + wc * qc, zd = om1 * pb.y + cb2.y + wd * qd;
+          *reinterpret_cast<float2*>(zout + ci + D.nx) = make_float2(zc2, zd);
+          acc[0] += (double)(__fdividef(cb2.x, wc) * zc2) + (double)(__fdividef(cb2.y, wd) * zd);
         }
       }
+      lt = ct;
+      lb = cb2;
+      pt = nt0;
+      pb = nb0;
       ci += plane;
     }
     seq += nplanes;
@@ -534,55 +533,73 @@ __global__ void __launch_bounds__(NTHR, 2) k_mg_fine(const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------
-// CG vector kernels of the multigrid-preconditioned iteration (no a_P needed -> no code bytes read)
-//   k_cg_update_mg: x += alpha p;  r -= alpha q;  partial r.r          (48 B per cell)
-//   k_cg_dir_mg   : p = z + beta p   (first = 1: p = z)                 (24 B per cell)
+// CG vector kernels of the multigrid-preconditioned iteration.  Rows round-robin over a fixed grid.
+//   k_cg_update_mg: x += alpha p;  r -= alpha q;  u = omega r / d (FP32);  partial r.r     (53 B per cell)
+//   k_mg_make_u   : u = omega r / d alone (after the initial residual, and for the test hook)
+//   k_cg_dir_mg   : p = z + beta p   (first = 1: p = z; z is FP32)                          (20 B per cell)
+// u rows are `pitch` floats apart (multiple of 4: a TMA row stride must be a multiple of 16 bytes);
+// u points at plane 0 of a field with one halo plane below.
 // ------------------------------------------------------------------------------------------------
+template <int UPDATE>
 __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ x, double* __restrict__ r,
-                                                      const double* __restrict__ p, const double* __restrict__ q, long n2,
-                                                      long n, const Scal* __restrict__ S, int par,
+                                                      const double* __restrict__ p, const double* __restrict__ q,
+                                                      const uint8_t* __restrict__ code, const float* __restrict__ gtab,
+                                                      float* __restrict__ u, int pitch, const Dom D,
+                                                      const Scal* __restrict__ S, int par,
                                                       double* __restrict__ partials) {
   __shared__ double red[32 * 2];
+  __shared__ float tab[27 * 128];  // omega / d
   if (S->done) return;
-  const double alpha = S->rz[par] / S->pq;
+  for (int e = threadIdx.x; e < MG_TAB; e += blockDim.x) tab[e] = gtab[e];
+  __syncthreads();
+  const double alpha = UPDATE ? S->rz[par] / S->pq : 0.0;
+  const long rows = (long)D.ny * D.nz;
   double acc[2] = {0, 0};
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
-    double2 vx = reinterpret_cast<double2*>(x)[i], vr = reinterpret_cast<double2*>(r)[i];
-    const double2 vp = reinterpret_cast<const double2*>(p)[i], vq = reinterpret_cast<const double2*>(q)[i];
-    vx.x += alpha * vp.x;
-    vx.y += alpha * vp.y;
-    vr.x -= alpha * vq.x;
-    vr.y -= alpha * vq.y;
-    acc[1] += vr.x * vr.x + vr.y * vr.y;
-    reinterpret_cast<double2*>(x)[i] = vx;
-    reinterpret_cast<double2*>(r)[i] = vr;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % D.ny), z = (int)(row / D.ny);
+    const float* trow = tab + ((3 * mg_cls(y, D.ny) + 9 * mg_cls(D.z0 + z, D.nzg)) << 7);
+    const long base = row * D.nx;
+    float* urow = u + ((long)z * D.ny + y) * pitch;
+    for (int xx = threadIdx.x * 2; xx < D.nx; xx += blockDim.x * 2) {
+      const long i = base + xx;
+      double2 vr = *reinterpret_cast<const double2*>(r + i);
+      if (UPDATE) {
+        double2 vx = *reinterpret_cast<const double2*>(x + i);
+        const double2 vp = *reinterpret_cast<const double2*>(p + i), vq = *reinterpret_cast<const double2*>(q + i);
+        vx.x += alpha * vp.x;
+        vx.y += alpha * vp.y;
+        vr.x -= alpha * vq.x;
+        vr.y -= alpha * vq.y;
+        acc[1] += vr.x * vr.x + vr.y * vr.y;
+        *reinterpret_cast<double2*>(x + i) = vx;
+        *reinterpret_cast<double2*>(r + i) = vr;
+      }
+      const unsigned cc = *reinterpret_cast<const unsigned short*>(code + i);
+      const float t0 = trow[(mg_cls(xx, D.nx) << 7) | (cc & 127u)], t1 = trow[(mg_cls(xx + 1, D.nx) << 7) | ((cc >> 8) & 127u)];
+      *reinterpret_cast<float2*>(urow + xx) = make_float2((float)vr.x * t0, (float)vr.y * t1);
+    }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const long i = n - 1;
-    x[i] += alpha * p[i];
-    const double ri = r[i] - alpha * q[i];
-    r[i] = ri;
-    acc[1] += ri * ri;
-  }
-  block_sum<2>(acc, red);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x * 2 + 0] = 0.0;
-    partials[blockIdx.x * 2 + 1] = acc[1];
+  if (UPDATE) {
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x * 2 + 0] = 0.0;
+      partials[blockIdx.x * 2 + 1] = acc[1];
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ p, const double* __restrict__ z, long n2, long n,
+__global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ p, const float* __restrict__ z, long n2, long n,
                                                    const Scal* __restrict__ S, int par, int first) {
   if (S->done) return;
   const double beta = first ? 0.0 : S->rz[par ^ 1] / S->rz[par];
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
-    const double2 vz = reinterpret_cast<const double2*>(z)[i];
+    const float2 vz = reinterpret_cast<const float2*>(z)[i];
     double2 vp = reinterpret_cast<double2*>(p)[i];
-    vp.x = vz.x + beta * vp.x;
-    vp.y = vz.y + beta * vp.y;
+    vp.x = (double)vz.x + beta * vp.x;
+    vp.y = (double)vz.y + beta * vp.y;
     reinterpret_cast<double2*>(p)[i] = vp;
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = z[n - 1] + beta * p[n - 1];
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = (double)z[n - 1] + beta * p[n - 1];
 }
 
 // scalar steps of the multigrid-preconditioned iteration

@@ -49,6 +49,8 @@ Coef make_coef(int nx, int ny, int nzg, const keffb200_params& P) {
   return C;
 }
 
+static int mg_pitch(int nx) { return (nx + 3) / 4 * 4; }
+
 static int ensure_ws(const Dom& D) {
   Ctx& c = ctx();
   const size_t plane = (size_t)D.nx * D.ny, need = plane * (D.nz + 2);
@@ -70,8 +72,16 @@ static int ensure_ws(const Dom& D) {
     if (c.z) cudaFree(c.z);
     c.z = nullptr;
     c.cap_z = 0;
-    KB_CUDA(cudaMalloc(&c.z, plane * D.nz * sizeof(double)));
+    KB_CUDA(cudaMalloc(&c.z, plane * D.nz * sizeof(float)));
     c.cap_z = plane * D.nz;
+  }
+  const size_t need_u = (size_t)mg_pitch(D.nx) * D.ny * (D.nz + 2);
+  if (need_u > c.cap_u) {
+    if (c.u) cudaFree(c.u);
+    c.u = nullptr;
+    c.cap_u = 0;
+    KB_CUDA(cudaMalloc(&c.u, need_u * sizeof(float)));
+    c.cap_u = need_u;
   }
   const size_t rows = (size_t)D.ny * D.nz;
   if (rows > c.cap_aux) {
@@ -210,16 +220,22 @@ static int stencil_launch(const Stencil& s, int which, double* o0, double* o1) {
 }
 
 
+static int vec_threads(int nx, int V) {
+  const int lanes = (nx + V - 1) / V;
+  return std::min(256, std::max(32, (lanes + 31) / 32 * 32));
+}
+
 // ---- multigrid preconditioner: hierarchy, plan, V-cycle -----------------------------------------
 struct Mg {
   bool on = false;
   int nlev = 0;                // stored levels 1..nlev; level nlev is the dense one
   MgLevel L[MG_MAX_LEVELS];    // L[0]: extent and coarsening flags of the voxel grid only
   int ndense = 0;
-  CUtensorMap tm_r;
+  CUtensorMap tm_u;
+  int pitch = 0;               // floats per row of u
   Plan plan{};
-  int grid = 0;
-  double omega = 0.9;
+  int grid = 0, gu = 0;        // CTAs of the stencil passes / of the row-wise vector kernels
+  float omega = 0.9f;
   Dom D{};
   Coef C{};
 };
@@ -266,6 +282,9 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
     c.cap_mg = floats;
   }
   if (!c.mg_inv) KB_CUDA(cudaMalloc(&c.mg_inv, (size_t)MG_DENSE_MAX * MG_DENSE_MAX * sizeof(double)));
+  if (!c.mg_tab) KB_CUDA(cudaMalloc(&c.mg_tab, (size_t)2 * MG_TAB * sizeof(float)));
+  k_mg_tables<<<(MG_TAB + 255) / 256, 256, 0, c.st>>>(c.mg_tab, C, D.nzg == 1, mg.omega);
+  KB_LAUNCHED();
   KB_CUDA(cudaMemsetAsync(c.mg_pool, 0, floats * sizeof(float), c.st));
   float* base = c.mg_pool;
   for (int k = 1; k <= mg.nlev; k++) {
@@ -296,17 +315,29 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.L[mg.nlev], c.mg_inv);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
-  // voxel-grid passes: tensor map on r, work plan (z chunks of even length so aggregates stay whole)
-  KB_TRY(make_tmap(&mg.tm_r, c.r, D));
-  static bool attr_done = false;
-  if (!attr_done) {
-    KB_CUDA(cudaFuncSetAttribute(k_mg_fine<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
-    KB_CUDA(cudaFuncSetAttribute(k_mg_fine<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
-    attr_done = true;
+  // voxel-grid passes: tensor map on u, work plan (z chunks of even length so aggregates stay whole)
+  mg.pitch = mg_pitch(D.nx);
+  {
+    const size_t uplane = (size_t)mg.pitch * D.ny;
+    KB_CUDA(cudaMemsetAsync(c.u, 0, uplane * sizeof(float), c.st));
+    KB_CUDA(cudaMemsetAsync(c.u + uplane * (D.nz + 1), 0, uplane * sizeof(float), c.st));
+    cuuint64_t dims[3] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nz + 2};
+    cuuint64_t strides[2] = {(cuuint64_t)mg.pitch * 4, (cuuint64_t)uplane * 4};
+    cuuint32_t box[3] = {MG_BOXW, BOXH, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult rc = c.encode(&mg.tm_u, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.u, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(KEFFB200_ECUDA, "cuTensorMapEncodeTiled (u) failed (%d)", (int)rc);
   }
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_fine<1>, NTHR, MG_SMEM);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_fine<1>, NTHR, 0);
   occ = std::max(occ, 1);
+  {
+    const long rows = (long)D.ny * D.nz;
+    const int vt = vec_threads(D.nx, 2);
+    mg.gu = (int)std::min<long>(std::min<long>(rows, (long)c.sms * (2048 / vt)), (long)PARTIAL_SLOTS);
+  }
   const int G = c.sms * occ;
   Plan pl;
   pl.ntx = (D.nx + TX - 1) / TX;
@@ -335,14 +366,24 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   return 0;
 }
 
-// z = M r  (r: plane 0 of a field with zeroed halo planes; partial r.z lands in ctx().partials, stride 3)
-static int mg_vcycle(const Mg& mg, const double* r, double* z) {
+// u = omega r / d from a residual that some other kernel produced
+static int mg_make_u(const Mg& mg, double* r) {
   Ctx& c = ctx();
-  const float om = (float)mg.omega;
+  const int vt = vec_threads(mg.D.nx, 2);
+  k_cg_update_mg<0><<<mg.gu, vt, 0, c.st>>>(nullptr, r, nullptr, nullptr, c.code, c.mg_tab, c.u + (size_t)mg.pitch * mg.D.ny,
+                                            mg.pitch, mg.D, c.S, 0, c.partials);
+  KB_LAUNCHED();
+  return 0;
+}
+
+// z = M r, r given through u = omega r / d (ctx().u); partial r.z lands in ctx().partials, stride 3
+static int mg_vcycle(const Mg& mg, float* z) {
+  Ctx& c = ctx();
+  const float om = mg.omega;
   const MgLevel& L0 = mg.L[0];
   const MgLevel& L1 = mg.L[1];
-  MgFine mf{L1.e, L1.b, L1.nx, L1.ny, L0.fy, L0.fz, mg.omega};
-  k_mg_fine<0><<<mg.grid, NTHR, MG_SMEM, c.st>>>(mg.tm_r, r, c.code, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
+  MgFine mf{L1.e, L1.b, L1.nx, L1.ny, L1.nz, L0.fy, L0.fz, mg.omega};
+  k_mg_fine<0><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
   KB_LAUNCHED();
   for (int k = 1; k < mg.nlev; k++) {
     const MgLevel& L = mg.L[k];
@@ -363,16 +404,12 @@ static int mg_vcycle(const Mg& mg, const double* r, double* z) {
                                                                     L.e, om, 0, 0, c.S);
     KB_LAUNCHED();
   }
-  k_mg_fine<1><<<mg.grid, NTHR, MG_SMEM, c.st>>>(mg.tm_r, r, c.code, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
+  k_mg_fine<1><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int vec_threads(int nx, int V) {
-  const int lanes = (nx + V - 1) / V;
-  return std::min(256, std::max(32, (lanes + 31) / 32 * 32));
-}
 
 // ---- the solve ----------------------------------------------------------------------------------
 // d_mask_halo: (nz+2) planes (plane 0 and nz+1 are the slab neighbours' planes or don't-care);
@@ -412,11 +449,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   Stencil s;
   KB_TRY(stencil_setup(s, D, C, P.flags));
   Mg mg;
-  if (mg_eligible(D, P.flags)) {
-    KB_CUDA(cudaMemsetAsync(c.r, 0, plane * 8, c.st));
-    KB_CUDA(cudaMemsetAsync(c.r + plane * (D.nz + 1), 0, plane * 8, c.st));
-    KB_TRY(mg_setup(mg, D, C));
-  }
+  if (mg_eligible(D, P.flags)) KB_TRY(mg_setup(mg, D, C));
   const long n2 = (long)(n / 2);
   const int gm = mg_grid(n2);
   const long check_every = mg.on ? std::min<long>(P.check_every, 4) : P.check_every;
@@ -443,7 +476,8 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       k_step_init<<<1, 1, 0, c.st>>>(c.S);
       KB_LAUNCHED();
       if (mg.on) {  // p = z = M r, r.z
-        KB_TRY(mg_vcycle(mg, r, c.z));
+        KB_TRY(mg_make_u(mg, r));
+        KB_TRY(mg_vcycle(mg, c.z));
         k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
         KB_LAUNCHED();
         k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, 0);
@@ -463,13 +497,14 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       KB_LAUNCHED();
       KB_TRY(allreduce_tmp(&c.S->pq, 1));
       if (mg.on) {
-        k_cg_update_mg<<<gm, 256, 0, c.st>>>(x, r, p, q, n2, (long)n, c.S, par, c.partials);
+        k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(x, r, p, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D,
+                                                  c.S, par, c.partials);
         KB_LAUNCHED();
-        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gm, 1, c.S);
+        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.gu, 1, c.S);
         KB_LAUNCHED();
         k_step_mg_rr<<<1, 1, 0, c.st>>>(c.S);
         KB_LAUNCHED();
-        KB_TRY(mg_vcycle(mg, r, c.z));
+        KB_TRY(mg_vcycle(mg, c.z));
         k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
         KB_LAUNCHED();
         k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, par ^ 1);
@@ -653,8 +688,13 @@ void keffb200_shutdown(void) {
   if (c.code) cudaFree(c.code);
   if (c.mask) cudaFree(c.mask);
   if (c.z) cudaFree(c.z);
+  if (c.u) cudaFree(c.u);
+  c.u = nullptr;
+  c.cap_u = 0;
   if (c.mg_pool) cudaFree(c.mg_pool);
   if (c.mg_inv) cudaFree(c.mg_inv);
+  if (c.mg_tab) cudaFree(c.mg_tab);
+  c.mg_tab = nullptr;
   c.z = nullptr;
   c.mg_pool = nullptr;
   c.mg_inv = nullptr;
@@ -864,9 +904,14 @@ int keffb200_precond(const uint8_t* solid, int nx, int ny, int nz, const keffb20
   KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
   Mg mg;
   KB_TRY(mg_setup(mg, D, C));
-  KB_TRY(mg_vcycle(mg, c.r + plane, c.z));
-  KB_CUDA(cudaMemcpyAsync(zout, c.z, n * 8, cudaMemcpyDeviceToHost, c.st));
+  KB_TRY(mg_make_u(mg, c.r + plane));
+  KB_TRY(mg_vcycle(mg, c.z));
+  KB_CUDA(cudaGetLastError());
+  // widen the FP32 result on the host side of the hook (q is free here)
+  std::vector<float> zf(n);
+  KB_CUDA(cudaMemcpyAsync(zf.data(), c.z, n * sizeof(float), cudaMemcpyDeviceToHost, c.st));
   KB_CUDA(cudaStreamSynchronize(c.st));
+  for (size_t i = 0; i < n; i++) zout[i] = zf[i];
   return 0;
 }
 
