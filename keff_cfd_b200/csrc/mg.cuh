@@ -135,74 +135,82 @@ __global__ void k_mg_dinv(MgLevel L, int lo) {
 // stored-level smoothing passes (FP32, neighbours through L1/L2; these levels hold <= 1/8 of the cells)
 // ------------------------------------------------------------------------------------------------
 // lo/hi: the level's z-halo planes (b, dinv, e of the slab neighbours) are valid
-__device__ __forceinline__ float mg_u(const MgLevelView& L, const float* __restrict__ b, long i, float om) {
+__device__ __forceinline__ float mg_u(const MgLevelView& L, const float* __restrict__ b, int i, float om) {
   return om * b[i] * L.dinv[i];
 }
 
+// Thread layout of the stored-level passes: a block is bx (32..256, covering a row of the output
+// when it fits) x 256/bx threads; blockIdx.x strides over y, blockIdx.y over z -- 32-bit index arithmetic,
+// no division.
 // restricted residual after the pre-smoothing sweep: bc = P^T ((1-omega) b + sum_f c_f u_nb)
 __global__ void __launch_bounds__(256) k_mg_pre(const MgLevelView L, const float* __restrict__ b, int fx, int fy, int fz,
                                                 int cnx, int cny, int cnz, float* __restrict__ bc, float om, int lo,
-                                                int hi, const Scal* __restrict__ S) {
+                                                int hi, int bx, const Scal* __restrict__ S) {
   if (S->done) return;
-  const long plane = (long)L.nx * L.ny;
-  const long nc = (long)cnx * cny * cnz;
-  for (long ic = blockIdx.x * (long)blockDim.x + threadIdx.x; ic < nc; ic += (long)gridDim.x * blockDim.x) {
-    const int X = (int)(ic % cnx);
-    const long t = ic / cnx;
-    const int Y = (int)(t % cny), Z = (int)(t / cny);
-    float acc = 0.f;
-    for (int dz = 0; dz <= fz; dz++) {
-      const int z = fz ? 2 * Z + dz : Z;
-      if (z >= L.nz) break;
-      for (int dy = 0; dy <= fy; dy++) {
-        const int y = fy ? 2 * Y + dy : Y;
-        if (y >= L.ny) break;
-        for (int dx = 0; dx <= fx; dx++) {
-          const int x = fx ? 2 * X + dx : X;
-          if (x >= L.nx) break;
-          const long i = ((long)z * L.ny + y) * L.nx + x;
-          float s = (1.f - om) * b[i];
-          if (x > 0) s += L.cx[i - 1] * mg_u(L, b, i - 1, om);
-          if (x < L.nx - 1) s += L.cx[i] * mg_u(L, b, i + 1, om);
-          if (y > 0) s += L.cy[i - L.nx] * mg_u(L, b, i - L.nx, om);
-          if (y < L.ny - 1) s += L.cy[i] * mg_u(L, b, i + L.nx, om);
-          if (z > 0 || lo) s += L.cz[i - plane] * mg_u(L, b, i - plane, om);
-          if (z < L.nz - 1 || hi) s += L.cz[i] * mg_u(L, b, i + plane, om);
-          acc += s;
+  const int plane = L.nx * L.ny;  // stored levels hold < 2^31 cells
+  const int tx = threadIdx.x & (bx - 1), trow = threadIdx.x / bx, rpb = blockDim.x / bx;  // bx: power of two
+  for (int Z = blockIdx.y; Z < cnz; Z += gridDim.y)
+  for (int Y = blockIdx.x * rpb + trow; Y < cny; Y += gridDim.x * rpb) {
+    const int crow = Z * cny + Y;
+    for (int X = tx; X < cnx; X += bx) {
+      float acc = 0.f;
+      for (int dz = 0; dz <= fz; dz++) {
+        const int z = fz ? 2 * Z + dz : Z;
+        if (z >= L.nz) break;
+        for (int dy = 0; dy <= fy; dy++) {
+          const int y = fy ? 2 * Y + dy : Y;
+          if (y >= L.ny) break;
+          for (int dx = 0; dx <= fx; dx++) {
+            const int x = fx ? 2 * X + dx : X;
+            if (x >= L.nx) break;
+            const int i = (z * L.ny + y) * L.nx + x;
+            float s = (1.f - om) * b[i];
+            if (x > 0) s += L.cx[i - 1] * mg_u(L, b, i - 1, om);
+            if (x < L.nx - 1) s += L.cx[i] * mg_u(L, b, i + 1, om);
+            if (y > 0) s += L.cy[i - L.nx] * mg_u(L, b, i - L.nx, om);
+            if (y < L.ny - 1) s += L.cy[i] * mg_u(L, b, i + L.nx, om);
+            if (z > 0 || lo) s += L.cz[i - plane] * mg_u(L, b, i - plane, om);
+            if (z < L.nz - 1 || hi) s += L.cz[i] * mg_u(L, b, i + plane, om);
+            acc += s;
+          }
         }
       }
+      bc[crow * cnx + X] = acc;
     }
-    bc[ic] = acc;
   }
-}
-
-__device__ __forceinline__ float mg_v(const MgLevelView& L, const float* __restrict__ b, const float* __restrict__ ec,
-                                      int x, int y, int z, long i, int fx, int fy, int fz, int cnx, int cny,
-                                      float om) {
-  const int X = fx ? x >> 1 : x, Y = fy ? y >> 1 : y, Z = fz ? z >> 1 : z;  // z = -1 -> Z = -1 (halo plane)
-  return om * b[i] * L.dinv[i] + ec[((long)Z * cny + Y) * cnx + X];
 }
 
 // e = (1-omega) v_P + omega D^-1_P (b_P + sum_f c_f v_nb),  v = omega D^-1 b + P ec
 __global__ void __launch_bounds__(256) k_mg_post(const MgLevelView L, const float* __restrict__ b,
                                                  const float* __restrict__ ec, int fx, int fy, int fz, int cnx, int cny,
-                                                 float* __restrict__ e, float om, int lo, int hi,
+                                                 float* __restrict__ e, float om, int lo, int hi, int bx,
                                                  const Scal* __restrict__ S) {
   if (S->done) return;
-  const long plane = (long)L.nx * L.ny, n = plane * L.nz;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % L.nx);
-    const long t = i / L.nx;
-    const int y = (int)(t % L.ny), z = (int)(t / L.ny);
-    float s = b[i];
-    if (x > 0) s += L.cx[i - 1] * mg_v(L, b, ec, x - 1, y, z, i - 1, fx, fy, fz, cnx, cny, om);
-    if (x < L.nx - 1) s += L.cx[i] * mg_v(L, b, ec, x + 1, y, z, i + 1, fx, fy, fz, cnx, cny, om);
-    if (y > 0) s += L.cy[i - L.nx] * mg_v(L, b, ec, x, y - 1, z, i - L.nx, fx, fy, fz, cnx, cny, om);
-    if (y < L.ny - 1) s += L.cy[i] * mg_v(L, b, ec, x, y + 1, z, i + L.nx, fx, fy, fz, cnx, cny, om);
-    if (z > 0 || lo) s += L.cz[i - plane] * mg_v(L, b, ec, x, y, z - 1, i - plane, fx, fy, fz, cnx, cny, om);
-    if (z < L.nz - 1 || hi) s += L.cz[i] * mg_v(L, b, ec, x, y, z + 1, i + plane, fx, fy, fz, cnx, cny, om);
-    const float vP = mg_v(L, b, ec, x, y, z, i, fx, fy, fz, cnx, cny, om);
-    e[i] = (1.f - om) * vP + om * L.dinv[i] * s;
+  const int plane = L.nx * L.ny, cplane = cnx * cny;
+  const int tx = threadIdx.x & (bx - 1), trow = threadIdx.x / bx, rpb = blockDim.x / bx;  // bx: power of two
+  for (int z = blockIdx.y; z < L.nz; z += gridDim.y)
+  for (int y = blockIdx.x * rpb + trow; y < L.ny; y += gridDim.x * rpb) {
+    const int row = z * L.ny + y;
+    const int Y = fy ? y >> 1 : y, Z = fz ? z >> 1 : z;
+    const float* e0 = ec + Z * cplane + Y * cnx;                                 // my aggregate row
+    const float* eN = ec + Z * cplane + (fy ? (y - 1) >> 1 : y - 1) * cnx;       // of the cell north / south
+    const float* eS = ec + Z * cplane + (fy ? (y + 1) >> 1 : y + 1) * cnx;
+    const float* eF = ec + (fz ? (z - 1) >> 1 : z - 1) * cplane + Y * cnx;       // of the cell in front / behind
+    const float* eB = ec + (fz ? (z + 1) >> 1 : z + 1) * cplane + Y * cnx;
+    for (int x = tx; x < L.nx; x += bx) {
+      const int i = row * L.nx + x;
+      const int X = fx ? x >> 1 : x;
+      float s = b[i];
+      if (x > 0) s += L.cx[i - 1] * (mg_u(L, b, i - 1, om) + e0[fx ? (x - 1) >> 1 : x - 1]);
+      if (x < L.nx - 1) s += L.cx[i] * (mg_u(L, b, i + 1, om) + e0[fx ? (x + 1) >> 1 : x + 1]);
+      if (y > 0) s += L.cy[i - L.nx] * (mg_u(L, b, i - L.nx, om) + eN[X]);
+      if (y < L.ny - 1) s += L.cy[i] * (mg_u(L, b, i + L.nx, om) + eS[X]);
+      if (z > 0 || lo) s += L.cz[i - plane] * (mg_u(L, b, i - plane, om) + eF[X]);
+      if (z < L.nz - 1 || hi) s += L.cz[i] * (mg_u(L, b, i + plane, om) + eB[X]);
+      const float di = L.dinv[i];
+      const float vP = om * b[i] * di + e0[X];
+      e[i] = (1.f - om) * vP + om * di * s;
+    }
   }
 }
 

@@ -246,6 +246,18 @@ static bool mg_eligible(const Dom& D, int flags) {
 }
 
 static int mg_grid(long n) { return (int)std::max<long>(1, std::min<long>((n + 255) / 256, (long)ctx().sms * 8)); }
+// block shape of the stored-level passes: bx threads along x, 256/bx rows per block
+static int mg_bx(int nx) {
+  int bx = 32;
+  while (bx < nx && bx < 256) bx *= 2;
+  return bx;
+}
+static dim3 mg_row_grid(int nx, int ny, int nz) {
+  const int rpb = 256 / mg_bx(nx);
+  const int gx = (ny + rpb - 1) / rpb;                                       // blocks covering y once
+  const int gz = std::max(1, std::min(nz, (ctx().sms * 8 + gx - 1) / gx));   // ... and enough z for ~8 CTAs per SM
+  return dim3((unsigned)gx, (unsigned)std::min(gz, 65535), 1);
+}
 
 static MgLevelView mg_view(const MgLevel& L) { return MgLevelView{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.dinv}; }
 
@@ -388,8 +400,8 @@ static int mg_vcycle(const Mg& mg, float* z) {
   for (int k = 1; k < mg.nlev; k++) {
     const MgLevel& L = mg.L[k];
     const MgLevel& N = mg.L[k + 1];
-    k_mg_pre<<<mg_grid((long)N.nx * N.ny * N.nz), 256, 0, c.st>>>(mg_view(L), L.b, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
-                                                                   N.b, om, 0, 0, c.S);
+    k_mg_pre<<<mg_row_grid(N.nx, N.ny, N.nz), 256, 0, c.st>>>(mg_view(L), L.b, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
+                                                                      N.b, om, 0, 0, mg_bx(N.nx), c.S);
     KB_LAUNCHED();
   }
   {
@@ -400,8 +412,8 @@ static int mg_vcycle(const Mg& mg, float* z) {
   for (int k = mg.nlev - 1; k >= 1; k--) {
     const MgLevel& L = mg.L[k];
     const MgLevel& N = mg.L[k + 1];
-    k_mg_post<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(mg_view(L), L.b, N.e, L.fx, L.fy, L.fz, N.nx, N.ny,
-                                                                    L.e, om, 0, 0, c.S);
+    k_mg_post<<<mg_row_grid(L.nx, L.ny, L.nz), 256, 0, c.st>>>(mg_view(L), L.b, N.e, L.fx, L.fy, L.fz, N.nx, N.ny,
+                                                                       L.e, om, 0, 0, mg_bx(L.nx), c.S);
     KB_LAUNCHED();
   }
   k_mg_fine<1><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);

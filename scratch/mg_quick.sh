@@ -16,5 +16,5 @@ for r in rows[start:]:
     a = agg.setdefault(n, {}); a.setdefault(r[mi], []).append(v)
 for n, a in agg.items():
     t = a.get('gpu__time_duration.sum', [0]); ins = a.get('smsp__inst_executed.sum', [0])
-    if max(t) > 20000: print(f"{n:34s} n={len(t):3d} last {t[-1]/1e3:9.1f} us  inst {ins[-1]/1e6:8.1f} M")
+    if max(t) > 20000: print(f"{n:34s} n={len(t):3d} max {max(t)/1e3:9.1f} us  inst {max(ins)/1e6:8.1f} M  sum {sum(t)/1e3:9.1f} us")
 PY
