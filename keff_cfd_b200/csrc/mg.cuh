@@ -298,6 +298,7 @@ struct MgFine {
   float* b1;        // level-1 right-hand side (PRE)
   int nx1, ny1, nz1;
   int fy, fz;       // y / z coarsened (x always is: nx even >= 4)
+  int lo, hi;       // z-slabs: halo planes of u / e1 hold the lower / upper neighbour's values
   float omega;
 };
 
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     float nE0 = 0.f, nEW = 0.f, nEE = 0.f, nEN = 0.f, nES = 0.f;  // prefetched for the next aggregate plane
     auto load_E = [&](int Z, float& a0, float& aw, float& ae, float& an, float& as) {
       a0 = aw = ae = an = as = 0.f;
-      if (Z < 0 || Z >= M.nz1) return;
+      if ((Z < 0 && !(M.lo && Z == -1)) || (Z >= M.nz1 && !(M.hi && Z == M.nz1))) return;
       const float* ep = M.e1 + (long)Z * eplane + eoff;
       if (row0) a0 = ep[0];
       if (hW) aw = ep[-1];

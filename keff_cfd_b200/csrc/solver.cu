@@ -131,6 +131,29 @@ static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
   return 0;
 }
 
+// same for any plane-major array: plane0 = local plane 0, halo planes at -1 and nz
+static int exchange_planes(void* plane0, size_t plane_bytes, int nz, cudaStream_t st) {
+  Nccl& n = ctx().nccl;
+  if (n.world <= 1 || !n.comm || !ctx().dist_active) return 0;
+  char* b = (char*)plane0;
+  KB_TRY(nccl_check(n.GroupStart(), "ncclGroupStart"));
+  if (n.rank > 0) {
+    KB_TRY(nccl_check(n.Send(b, plane_bytes, /*ncclInt8*/ 0, n.rank - 1, n.comm, st), "ncclSend"));
+    KB_TRY(nccl_check(n.Recv(b - plane_bytes, plane_bytes, 0, n.rank - 1, n.comm, st), "ncclRecv"));
+  }
+  if (n.rank < n.world - 1) {
+    KB_TRY(nccl_check(n.Send(b + (size_t)(nz - 1) * plane_bytes, plane_bytes, 0, n.rank + 1, n.comm, st), "ncclSend"));
+    KB_TRY(nccl_check(n.Recv(b + (size_t)nz * plane_bytes, plane_bytes, 0, n.rank + 1, n.comm, st), "ncclRecv"));
+  }
+  KB_TRY(nccl_check(n.GroupEnd(), "ncclGroupEnd"));
+  return 0;
+}
+
+static int allgather_f32(const float* src, float* dst, size_t count) {
+  Nccl& n = ctx().nccl;
+  return nccl_check(n.AllGather(src, dst, count, /*ncclFloat32*/ 7, n.comm, ctx().st), "ncclAllGather");
+}
+
 // ---- stencil launcher ---------------------------------------------------------------------------
 struct Stencil {
   bool tma = false;
@@ -230,7 +253,10 @@ struct Mg {
   bool on = false;
   int nlev = 0;                // stored levels 1..nlev; level nlev is the dense one
   MgLevel L[MG_MAX_LEVELS];    // L[0]: extent and coarsening flags of the voxel grid only
-  int ndense = 0;
+  int ndense = 0;              // cells of the dense level (global)
+  int z0[MG_MAX_LEVELS] = {0}, nzg[MG_MAX_LEVELS] = {0};  // per level: first global plane of my slab, global planes
+  bool dist = false, lo = false, hi = false;              // z-slab mode; a neighbour below / above
+  MgLevel G{};                 // the dense level gathered over all ranks (== L[nlev] on one GPU)
   CUtensorMap tm_u;
   int pitch = 0;               // floats per row of u
   Plan plan{};
@@ -242,7 +268,7 @@ struct Mg {
 
 static bool mg_eligible(const Dom& D, int flags) {
   return !(flags & (KEFFB200_F_NO_MG | KEFFB200_F_NO_TMA)) && D.nx % 2 == 0 && D.nx >= 4 && D.ny >= 2 &&
-         (long)D.nx * D.ny * D.nz > MG_DENSE_MAX && !ctx().dist_active && ctx().encode != nullptr;
+         (long)D.nx * D.ny * D.nzg > MG_DENSE_MAX && ctx().encode != nullptr;
 }
 
 static int mg_grid(long n) { return (int)std::max<long>(1, std::min<long>((n + 255) / 256, (long)ctx().sms * 8)); }
@@ -265,27 +291,77 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   Ctx& c = ctx();
   mg.D = D;
   mg.C = C;
-  // extents
-  int nx = D.nx, ny = D.ny, nz = D.nz, l = 0;
+  Nccl& nc = c.nccl;
+  mg.dist = c.dist_active && nc.world > 1;
+  mg.lo = mg.dist && D.z0 > 0;
+  mg.hi = mg.dist && D.z0 + D.nz < D.nzg;
+  // z-slabs: an aggregate must not straddle two ranks, so z is coarsened only while every rank's first
+  // plane and plane count are even; equal slabs are required (the dense level is all-gathered)
+  int kz = 1 << 20;
+  if (mg.dist) {
+    int k = 0;
+    while (((D.z0 >> k) & 1) == 0 && ((D.nz >> k) & 1) == 0 && (D.nz >> k) > 1) k++;
+    c.hS->tmp[0] = k;
+    c.hS->tmp[1] = D.nz;
+    c.hS->tmp[2] = -D.nz;
+    KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
+    KB_TRY(nccl_check(nc.AllReduce(c.S->tmp, c.S->tmp, 3, /*ncclFloat64*/ 8, /*ncclMin*/ 3, nc.comm, c.st), "ncclAllReduce"));
+    KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
+    KB_CUDA(cudaStreamSynchronize(c.st));
+    if (c.hS->tmp[1] != -c.hS->tmp[2]) return 0;  // unequal slabs: stay on the diagonally preconditioned path
+    kz = (int)c.hS->tmp[0];
+  }
+  // extents.  Semi-coarsening: on the unit cube a grid with unequal cell counts has unequal cell sizes, and
+  // point smoothing only works along strongly coupled (small-h) directions, so a direction is coarsened
+  // only while its cell size is within 1.5x of the smallest one.  (The voxel-grid passes always coarsen
+  // x and y: they handle the 2x2 xy block of a thread as one aggregate.)
+  int nx = D.nx, ny = D.ny, nz = D.nz, nzg = D.nzg, z0 = D.z0, l = 0, zdone = 0;
+  double hx = 1.0 / nx, hy = 1.0 / ny, hz = 1.0 / nzg;
   size_t floats = 0;
   while (true) {
     MgLevel& L = mg.L[l];
     L.nx = nx;
     L.ny = ny;
     L.nz = nz;
-    L.fx = nx > 1;
-    L.fy = ny > 1;
-    L.fz = nz > 1;
+    const bool cx = nx > 1, cy = ny > 1, cz = mg.dist ? (zdone < kz && nz > 1) : nz > 1;
+    double hmin = 1e300;
+    if (cx) hmin = std::min(hmin, hx);
+    if (cy) hmin = std::min(hmin, hy);
+    if (cz) hmin = std::min(hmin, hz);
+    if (l == 0) {
+      L.fx = L.fy = 1;
+      L.fz = cz && hz < 1.5 * std::min(hx, hy);
+    } else {
+      L.fx = cx && hx < 1.5 * hmin;
+      L.fy = cy && hy < 1.5 * hmin;
+      L.fz = cz && hz < 1.5 * hmin;
+    }
+    mg.z0[l] = z0;
+    mg.nzg[l] = nzg;
     if (l > 0) floats += 7 * (((size_t)nx * ny * (nz + 2) + 31) / 32 * 32);
-    if (l > 0 && (long)nx * ny * nz <= MG_DENSE_MAX) break;
+    if (l > 0 && (long)nx * ny * nzg <= MG_DENSE_MAX) break;
+    if (!L.fx && !L.fy && !L.fz) return 0;  // cannot get down to a dense level (only with odd slabs)
     if (l + 1 >= MG_MAX_LEVELS) return fail(KEFFB200_EINVAL, "multigrid hierarchy too deep");
-    nx = (nx + 1) / 2;
-    ny = (ny + 1) / 2;
-    nz = (nz + 1) / 2;
+    if (L.fx) {
+      nx = (nx + 1) / 2;
+      hx *= 2;
+    }
+    if (L.fy) {
+      ny = (ny + 1) / 2;
+      hy *= 2;
+    }
+    if (L.fz) {
+      nz = (nz + 1) / 2;
+      nzg = (nzg + 1) / 2;
+      z0 /= 2;
+      hz *= 2;
+      zdone++;
+    }
     l++;
   }
   mg.nlev = l;
-  mg.ndense = mg.L[l].nx * mg.L[l].ny * mg.L[l].nz;
+  mg.ndense = mg.L[l].nx * mg.L[l].ny * nzg;
+  floats += 6 * MG_DENSE_MAX;  // gathered dense level
   if (floats > c.cap_mg) {
     if (c.mg_pool) cudaFree(c.mg_pool);
     c.mg_pool = nullptr;
@@ -308,6 +384,16 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       base += stride;
     }
   }
+  mg.G = mg.L[mg.nlev];
+  if (mg.dist) {
+    mg.G.nz = mg.nzg[mg.nlev];
+    float** arr[6] = {&mg.G.cx, &mg.G.cy, &mg.G.cz, &mg.G.wsum, &mg.G.b, &mg.G.e};
+    for (int a = 0; a < 6; a++) {
+      *arr[a] = base;
+      base += MG_DENSE_MAX;
+    }
+    mg.G.dinv = nullptr;
+  }
   // operators
   {
     const MgLevel& L0 = mg.L[0];
@@ -321,10 +407,21 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       k_mg_coarsen_level<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(mg.L[k - 1], L);
       KB_LAUNCHED();
     }
-    k_mg_dinv<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(L, 0);
+    const size_t pb = (size_t)L.nx * L.ny * sizeof(float);
+    KB_TRY(exchange_planes(L.cz, pb, L.nz, c.st));  // cz[-1]: the face towards the lower neighbour
+    k_mg_dinv<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(L, mg.lo);
     KB_LAUNCHED();
+    KB_TRY(exchange_planes(L.dinv, pb, L.nz, c.st));
   }
-  k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.L[mg.nlev], c.mg_inv);
+  if (mg.dist) {
+    const MgLevel& L = mg.L[mg.nlev];
+    const size_t cnt = (size_t)L.nx * L.ny * L.nz;
+    KB_TRY(allgather_f32(L.cx, mg.G.cx, cnt));
+    KB_TRY(allgather_f32(L.cy, mg.G.cy, cnt));
+    KB_TRY(allgather_f32(L.cz, mg.G.cz, cnt));
+    KB_TRY(allgather_f32(L.wsum, mg.G.wsum, cnt));
+  }
+  k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.G, c.mg_inv);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
   // voxel-grid passes: tensor map on u, work plan (z chunks of even length so aggregates stay whole)
@@ -388,40 +485,51 @@ static int mg_make_u(const Mg& mg, double* r) {
   return 0;
 }
 
-// z = M r, r given through u = omega r / d (ctx().u); partial r.z lands in ctx().partials, stride 3
+// z = M r, r given through u = omega r / d (ctx().u); partial r.z lands in ctx().partials, stride 3.
+// z-slabs: every pass that reads a neighbour plane is preceded by the exchange of that array's halo planes.
 static int mg_vcycle(const Mg& mg, float* z) {
   Ctx& c = ctx();
   const float om = mg.omega;
+  const int lo = mg.lo, hi = mg.hi;
   const MgLevel& L0 = mg.L[0];
   const MgLevel& L1 = mg.L[1];
-  MgFine mf{L1.e, L1.b, L1.nx, L1.ny, L1.nz, L0.fy, L0.fz, mg.omega};
+  MgFine mf{L1.e, L1.b, L1.nx, L1.ny, L1.nz, L0.fy, L0.fz, lo, hi, mg.omega};
+  KB_TRY(exchange_planes(c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
   k_mg_fine<0><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
   KB_LAUNCHED();
   for (int k = 1; k < mg.nlev; k++) {
     const MgLevel& L = mg.L[k];
     const MgLevel& N = mg.L[k + 1];
+    KB_TRY(exchange_planes(L.b, (size_t)L.nx * L.ny * sizeof(float), L.nz, c.st));
     k_mg_pre<<<mg_row_grid(N.nx, N.ny, N.nz), 256, 0, c.st>>>(mg_view(L), L.b, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
-                                                                      N.b, om, 0, 0, mg_bx(N.nx), c.S);
+                                                               N.b, om, lo, hi, mg_bx(N.nx), c.S);
     KB_LAUNCHED();
   }
   {
     const MgLevel& L = mg.L[mg.nlev];
-    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, L.b, L.e, mg.ndense, c.S);
+    if (mg.dist) KB_TRY(allgather_f32(L.b, mg.G.b, (size_t)L.nx * L.ny * L.nz));
+    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, mg.G.b, mg.G.e, mg.ndense, c.S);
     KB_LAUNCHED();
+    if (mg.dist) {  // my planes of the global correction, plus one plane either side where it exists
+      const size_t plane = (size_t)L.nx * L.ny;
+      const int z0 = mg.z0[mg.nlev], a = std::max(z0 - 1, 0), b = std::min(z0 + L.nz + 1, mg.nzg[mg.nlev]);
+      KB_CUDA(cudaMemcpyAsync(L.e + (ptrdiff_t)(a - z0) * (ptrdiff_t)plane, mg.G.e + (size_t)a * plane,
+                              (size_t)(b - a) * plane * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+    }
   }
   for (int k = mg.nlev - 1; k >= 1; k--) {
     const MgLevel& L = mg.L[k];
     const MgLevel& N = mg.L[k + 1];
     k_mg_post<<<mg_row_grid(L.nx, L.ny, L.nz), 256, 0, c.st>>>(mg_view(L), L.b, N.e, L.fx, L.fy, L.fz, N.nx, N.ny,
-                                                                       L.e, om, 0, 0, mg_bx(L.nx), c.S);
+                                                                L.e, om, lo, hi, mg_bx(L.nx), c.S);
     KB_LAUNCHED();
+    KB_TRY(exchange_planes(L.e, (size_t)L.nx * L.ny * sizeof(float), L.nz, c.st));
   }
   k_mg_fine<1><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
   return 0;
 }
-
 
 // ---- the solve ----------------------------------------------------------------------------------
 // d_mask_halo: (nz+2) planes (plane 0 and nz+1 are the slab neighbours' planes or don't-care);
@@ -492,6 +600,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
         KB_TRY(mg_vcycle(mg, c.z));
         k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
         KB_LAUNCHED();
+        KB_TRY(allreduce_tmp(c.S->tmp, 1));
         k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, 0);
         KB_LAUNCHED();
         k_cg_dir_mg<<<gm, 256, 0, c.st>>>(p, c.z, n2, (long)n, c.S, 0, 1);
@@ -514,11 +623,13 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
         KB_LAUNCHED();
         k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.gu, 1, c.S);
         KB_LAUNCHED();
+        KB_TRY(allreduce_tmp(c.S->tmp, 2));
         k_step_mg_rr<<<1, 1, 0, c.st>>>(c.S);
         KB_LAUNCHED();
         KB_TRY(mg_vcycle(mg, c.z));
         k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
         KB_LAUNCHED();
+        KB_TRY(allreduce_tmp(c.S->tmp, 1));
         k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, par ^ 1);
         KB_LAUNCHED();
         k_cg_dir_mg<<<gm, 256, 0, c.st>>>(p, c.z, n2, (long)n, c.S, par, 0);
@@ -995,6 +1106,7 @@ static int nccl_load() {
   KB_SYM(CommInitRank, "ncclCommInitRank");
   KB_SYM(CommDestroy, "ncclCommDestroy");
   KB_SYM(AllReduce, "ncclAllReduce");
+  KB_SYM(AllGather, "ncclAllGather");
   KB_SYM(Send, "ncclSend");
   KB_SYM(Recv, "ncclRecv");
   KB_SYM(GroupStart, "ncclGroupStart");
