@@ -232,12 +232,16 @@ def main():
         out["stencil3d"] = {"workload": "configs[3]: 512^3 random binary volume, ks:kf 10:1", "kernel": "k_stencil_tma",
                             "ms_per_sweep": ms, "gcell_updates_per_s": n3 ** 3 / (ms * 1e-3) / 1e9, "bound": "hbm",
                             "achieved": gb, "peak": peak, "unit": "GB/s", "frac": gb / peak, "traffic": None}
+        api.solve3d(vol, p, want_T=False, device=local)               # first call allocates the workspace
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         r3 = api.solve3d(vol, p, want_T=False, device=local)
         torch.cuda.synchronize()
-        out["solve3d"] = {"workload": "configs[3]", "seconds": time.perf_counter() - t0, "solves_per_s": 1e3 / r3["gpu_ms"],
-                          "iters": r3["iters"], "keff": r3["keff"], "rel_residual": r3["rel_residual"],
-                          "status": r3["status"]}
+        out["solve3d"] = {"workload": "configs[3]", "solver": "CG preconditioned by a geometric multigrid V-cycle "
+                          "(FP32 cycle, FP64 CG vectors)", "seconds": time.perf_counter() - t0,
+                          "gpu_ms": r3["gpu_ms"], "solves_per_s": 1e3 / r3["gpu_ms"], "iters": r3["iters"],
+                          "ms_per_iter": r3["gpu_ms"] / max(r3["iters"], 1), "keff": r3["keff"],
+                          "rel_residual": r3["rel_residual"], "status": r3["status"]}
         del vol
 
     if rank == 0 and not args.no_cpu:
