@@ -53,12 +53,14 @@ struct Ctx {
   double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr;
   float* z = nullptr;    // preconditioned residual of the multigrid path (FP32, no halo planes)
   size_t cap_z = 0;
-  float* u = nullptr;    // omega r / a_P (FP32, pitched rows, one halo plane below and above)
+  float* u = nullptr;    // r / a_P (FP32, pitched rows, one halo plane below and above)
   size_t cap_u = 0;
+  float* xf[2] = {nullptr, nullptr};  // iterates of the voxel-grid smoothing sweeps (same layout as u; nu >= 2)
+  size_t cap_xf = 0;
   float* mg_pool = nullptr;  // stored multigrid levels (grow-only)
   size_t cap_mg = 0;         // floats
   double* mg_inv = nullptr;  // dense inverse of the coarsest level
-  float* mg_tab = nullptr;   // omega/d and d(1-omega)/omega by (position class, code byte)
+  float* mg_tab = nullptr;   // 1/d and d by (position class, code byte)
   uint8_t *code = nullptr, *mask = nullptr;
   size_t cap_aux = 0;  // doubles in qL/qR
   double *qL = nullptr, *qR = nullptr;

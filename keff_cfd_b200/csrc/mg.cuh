@@ -5,20 +5,25 @@
 // sweeps.  The linear system solved here is still exactly the reference's (DiscretizeMatrixCD2D/3D);
 // the V-cycle only changes how fast CG gets to its solution (iteration counts independent of N).
 //
-// Hierarchy: level 0 is the voxel grid (operator evaluated from the code bytes, FP64 vectors).
-// Level l+1 aggregates 2 cells per direction of level l (a lone last cell for odd sizes; directions
-// of extent 1 are left alone).  Transfer operators are piecewise constant: restriction = sum over the
-// aggregate, prolongation = copy to the aggregate's cells.  A coarse face conductance is the sum of
-// the fine face conductances crossing that coarse face, halved along coarsened directions (the
-// Galerkin product P^T A P of piecewise-constant transfers overestimates the coarse-grid stiffness by
-// 2; halving restores the re-discretised operator on a uniform medium).  Coarse levels are stored:
-// FP32 east/south/back face conductances, wall conductance, 1/a_P, right-hand side and correction.
-// Smoother: one weighted-Jacobi sweep before and after the coarse correction (same omega -> the cycle
-// is a symmetric positive definite operator, as CG requires).  With u = omega D^-1 b,
-//    pre :  residual  b - A u               = (1-omega) b_P + sum_f c_f u_nb        -> restricted
-//    post:  v = u + P e;   out = v + omega D^-1 (b - A v) = (1-omega) v_P + omega D^-1_P (b_P + sum_f c_f v_nb)
-// so each level costs two stencil passes and never stores u, v or the residual.
-// The coarsest level (<= 64 cells) is solved exactly by a dense inverse kept in global memory.
+// Hierarchy: level 0 is the voxel grid (operator evaluated from the code bytes).  Level l+1 aggregates
+// 2 cells per coarsened direction of level l (a lone last cell for odd sizes).  Transfer operators are
+// piecewise constant: restriction = sum over the aggregate, prolongation = copy to the aggregate's
+// cells.  A coarse face conductance is the sum of the fine face conductances crossing that coarse
+// face, halved along coarsened directions (the Galerkin product P^T A P of piecewise-constant
+// transfers overestimates the coarse-grid stiffness by 2; halving restores the re-discretised operator
+// on a uniform medium).  Coarse levels are stored: FP32 east/south/back face conductances, wall
+// conductance, 1/a_P, and the vectors of the cycle.  The whole cycle is FP32.
+//
+// Smoother: nu weighted-Jacobi sweeps with weights w_1..w_nu before the coarse correction and the
+// same weights in reverse order after it, so the cycle is a symmetric positive definite operator (what
+// CG needs); the weights are Chebyshev points for the upper part of the spectrum of D^-1 A.
+// Every level keeps its right-hand side in the scaled form u = D^-1 b.  One Jacobi sweep for A x = b is
+//     x' = (1-w) x + w u + w D^-1 sum_f c_f x_nb                                   ("sweep" pass)
+// and the residual of an iterate is  b - A x = D (u - x) + sum_f c_f x_nb          ("restrict" pass),
+// so every pass is one 7-point stencil over one field; the first iterate x_1 = w_1 u is never stored
+// (passes take a scale factor for their input), and the prolongated correction P e is never
+// materialised either (the first sweep after the coarse solve adds e of the right aggregate to each
+// value it reads).  The coarsest level (<= 64 cells) is solved by a dense inverse.
 #pragma once
 #include "kernels.cuh"
 
@@ -34,7 +39,15 @@ struct MgLevel {
   float *cx, *cy, *cz; // conductance of the face towards x+1 / y+1 / z+1 (0 at the domain end)
   float* wsum;         // fixed-temperature wall conductance of the cell (non-zero in the two wall columns)
   float* dinv;         // 1 / a_P
-  float *b, *e;        // right-hand side, correction
+  float *u, *e;        // scaled right-hand side D^-1 b (the dense level keeps b itself), correction
+  float *t0, *t1;      // iterates of the smoothing sweeps (nu >= 2)
+};
+
+// coefficients of one pass:  in = sc * (stored value) [+ e of its aggregate];
+//   sweep   : out = a in_P + b u_P + g D^-1_P sum_f c_f in_nb
+//   restrict: res = D_P (a in_P + b u_P) + g sum_f c_f in_nb
+struct MgPass {
+  float sc, a, b, g;
 };
 
 struct MgLevelView {
@@ -135,20 +148,21 @@ __global__ void k_mg_dinv(MgLevel L, int lo) {
 // stored-level smoothing passes (FP32, neighbours through L1/L2; these levels hold <= 1/8 of the cells)
 // ------------------------------------------------------------------------------------------------
 // lo/hi: the level's z-halo planes (b, dinv, e of the slab neighbours) are valid
-__device__ __forceinline__ float mg_u(const MgLevelView& L, const float* __restrict__ b, int i, float om) {
-  return om * b[i] * L.dinv[i];
-}
 
 // Thread layout of the stored-level passes: a block is bx (32..256, covering a row of the output
 // when it fits) x 256/bx threads; blockIdx.x strides over y, blockIdx.y over z -- 32-bit index arithmetic,
-// no division.
-// restricted residual after the pre-smoothing sweep: bc = P^T ((1-omega) b + sum_f c_f u_nb)
-__global__ void __launch_bounds__(256) k_mg_pre(const MgLevelView L, const float* __restrict__ b, int fx, int fy, int fz,
-                                                int cnx, int cny, int cnz, float* __restrict__ bc, float om, int lo,
-                                                int hi, int bx, const Scal* __restrict__ S) {
+// no division.  lo/hi: the z-halo planes of the input arrays hold the slab neighbours' values.
+// restrict pass: un[aggregate] = D^-1_next sum over the aggregate of  D_P (a in_P + b u_P) + g sum_f c_f in_nb
+// (dn == nullptr: the sum itself, for the dense level)
+__global__ void __launch_bounds__(256) k_mg_restrict(const MgLevelView L, const float* __restrict__ in,
+                                                     const float* __restrict__ u, const MgPass K, int fx, int fy, int fz,
+                                                     int cnx, int cny, int cnz, float* __restrict__ un,
+                                                     const float* __restrict__ dn, int lo, int hi, int bx,
+                                                     const Scal* __restrict__ S) {
   if (S->done) return;
   const int plane = L.nx * L.ny;  // stored levels hold < 2^31 cells
   const int tx = threadIdx.x & (bx - 1), trow = threadIdx.x / bx, rpb = blockDim.x / bx;  // bx: power of two
+  const float as = K.a * K.sc, gs = K.g * K.sc;
   for (int Z = blockIdx.y; Z < cnz; Z += gridDim.y)
   for (int Y = blockIdx.x * rpb + trow; Y < cny; Y += gridDim.x * rpb) {
     const int crow = Z * cny + Y;
@@ -164,52 +178,67 @@ __global__ void __launch_bounds__(256) k_mg_pre(const MgLevelView L, const float
             const int x = fx ? 2 * X + dx : X;
             if (x >= L.nx) break;
             const int i = (z * L.ny + y) * L.nx + x;
-            float s = (1.f - om) * b[i];
-            if (x > 0) s += L.cx[i - 1] * mg_u(L, b, i - 1, om);
-            if (x < L.nx - 1) s += L.cx[i] * mg_u(L, b, i + 1, om);
-            if (y > 0) s += L.cy[i - L.nx] * mg_u(L, b, i - L.nx, om);
-            if (y < L.ny - 1) s += L.cy[i] * mg_u(L, b, i + L.nx, om);
-            if (z > 0 || lo) s += L.cz[i - plane] * mg_u(L, b, i - plane, om);
-            if (z < L.nz - 1 || hi) s += L.cz[i] * mg_u(L, b, i + plane, om);
-            acc += s;
+            float q = 0.f;
+            if (x > 0) q += L.cx[i - 1] * in[i - 1];
+            if (x < L.nx - 1) q += L.cx[i] * in[i + 1];
+            if (y > 0) q += L.cy[i - L.nx] * in[i - L.nx];
+            if (y < L.ny - 1) q += L.cy[i] * in[i + L.nx];
+            if (z > 0 || lo) q += L.cz[i - plane] * in[i - plane];
+            if (z < L.nz - 1 || hi) q += L.cz[i] * in[i + plane];
+            acc += __fdividef(as * in[i] + K.b * u[i], L.dinv[i]) + gs * q;
           }
         }
       }
-      bc[crow * cnx + X] = acc;
+      const int ic = crow * cnx + X;
+      un[ic] = dn ? acc * dn[ic] : acc;
     }
   }
 }
 
-// e = (1-omega) v_P + omega D^-1_P (b_P + sum_f c_f v_nb),  v = omega D^-1 b + P ec
-__global__ void __launch_bounds__(256) k_mg_post(const MgLevelView L, const float* __restrict__ b,
-                                                 const float* __restrict__ ec, int fx, int fy, int fz, int cnx, int cny,
-                                                 float* __restrict__ e, float om, int lo, int hi, int bx,
-                                                 const Scal* __restrict__ S) {
+// sweep pass: out = a in_P + b u_P + g D^-1_P sum_f c_f in_nb,  in = sc * stored [+ ec of the aggregate]
+template <int ADD_E>
+__global__ void __launch_bounds__(256) k_mg_sweep(const MgLevelView L, const float* __restrict__ in,
+                                                  const float* __restrict__ u, const float* __restrict__ ec,
+                                                  const MgPass K, int fx, int fy, int fz, int cnx, int cny,
+                                                  float* __restrict__ out, int lo, int hi, int bx,
+                                                  const Scal* __restrict__ S) {
   if (S->done) return;
   const int plane = L.nx * L.ny, cplane = cnx * cny;
   const int tx = threadIdx.x & (bx - 1), trow = threadIdx.x / bx, rpb = blockDim.x / bx;  // bx: power of two
+  const float sc = K.sc;
   for (int z = blockIdx.y; z < L.nz; z += gridDim.y)
   for (int y = blockIdx.x * rpb + trow; y < L.ny; y += gridDim.x * rpb) {
     const int row = z * L.ny + y;
     const int Y = fy ? y >> 1 : y, Z = fz ? z >> 1 : z;
-    const float* e0 = ec + Z * cplane + Y * cnx;                                 // my aggregate row
-    const float* eN = ec + Z * cplane + (fy ? (y - 1) >> 1 : y - 1) * cnx;       // of the cell north / south
-    const float* eS = ec + Z * cplane + (fy ? (y + 1) >> 1 : y + 1) * cnx;
-    const float* eF = ec + (fz ? (z - 1) >> 1 : z - 1) * cplane + Y * cnx;       // of the cell in front / behind
-    const float* eB = ec + (fz ? (z + 1) >> 1 : z + 1) * cplane + Y * cnx;
+    const float *e0 = nullptr, *eN = nullptr, *eS = nullptr, *eF = nullptr, *eB = nullptr;
+    if (ADD_E) {
+      e0 = ec + Z * cplane + Y * cnx;                                 // my aggregate row
+      eN = ec + Z * cplane + (fy ? (y - 1) >> 1 : y - 1) * cnx;       // of the cell north / south
+      eS = ec + Z * cplane + (fy ? (y + 1) >> 1 : y + 1) * cnx;
+      eF = ec + (fz ? (z - 1) >> 1 : z - 1) * cplane + Y * cnx;       // of the cell in front / behind
+      eB = ec + (fz ? (z + 1) >> 1 : z + 1) * cplane + Y * cnx;
+    }
     for (int x = tx; x < L.nx; x += bx) {
       const int i = row * L.nx + x;
       const int X = fx ? x >> 1 : x;
-      float s = b[i];
-      if (x > 0) s += L.cx[i - 1] * (mg_u(L, b, i - 1, om) + e0[fx ? (x - 1) >> 1 : x - 1]);
-      if (x < L.nx - 1) s += L.cx[i] * (mg_u(L, b, i + 1, om) + e0[fx ? (x + 1) >> 1 : x + 1]);
-      if (y > 0) s += L.cy[i - L.nx] * (mg_u(L, b, i - L.nx, om) + eN[X]);
-      if (y < L.ny - 1) s += L.cy[i] * (mg_u(L, b, i + L.nx, om) + eS[X]);
-      if (z > 0 || lo) s += L.cz[i - plane] * (mg_u(L, b, i - plane, om) + eF[X]);
-      if (z < L.nz - 1 || hi) s += L.cz[i] * (mg_u(L, b, i + plane, om) + eB[X]);
-      const float di = L.dinv[i];
-      const float vP = om * b[i] * di + e0[X];
-      e[i] = (1.f - om) * vP + om * di * s;
+      float q = 0.f;
+      if (ADD_E) {
+        if (x > 0) q += L.cx[i - 1] * (sc * in[i - 1] + e0[fx ? (x - 1) >> 1 : x - 1]);
+        if (x < L.nx - 1) q += L.cx[i] * (sc * in[i + 1] + e0[fx ? (x + 1) >> 1 : x + 1]);
+        if (y > 0) q += L.cy[i - L.nx] * (sc * in[i - L.nx] + eN[X]);
+        if (y < L.ny - 1) q += L.cy[i] * (sc * in[i + L.nx] + eS[X]);
+        if (z > 0 || lo) q += L.cz[i - plane] * (sc * in[i - plane] + eF[X]);
+        if (z < L.nz - 1 || hi) q += L.cz[i] * (sc * in[i + plane] + eB[X]);
+        out[i] = K.a * (sc * in[i] + e0[X]) + K.b * u[i] + K.g * L.dinv[i] * q;
+      } else {
+        if (x > 0) q += L.cx[i - 1] * in[i - 1];
+        if (x < L.nx - 1) q += L.cx[i] * in[i + 1];
+        if (y > 0) q += L.cy[i - L.nx] * in[i - L.nx];
+        if (y < L.ny - 1) q += L.cy[i] * in[i + L.nx];
+        if (z > 0 || lo) q += L.cz[i - plane] * in[i - plane];
+        if (z < L.nz - 1 || hi) q += L.cz[i] * in[i + plane];
+        out[i] = K.a * sc * in[i] + K.b * u[i] + K.g * sc * L.dinv[i] * q;
+      }
     }
   }
 }
@@ -274,19 +303,21 @@ __global__ void __launch_bounds__(MG_DENSE_MAX) k_mg_dense_apply(const double* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// voxel-grid (level 0) passes.  The whole preconditioner works in FP32: the CG update kernel leaves
-//     u = omega r / a_P     (FP32, pitched rows, one halo plane below and above)
-// next to the FP64 residual, and the two passes below are plain 7-point stencils on u with the same
-// tiling as k_stencil_tma (a CTA marches a 64x16 xy tile in z; planes of u arrive by TMA in a
-// shared-memory ring, zero-filled outside the domain, so a face towards the outside multiplies a
-// zero and needs no boundary logic).  With d = a_P rounded to FP32 (table indexed by position class
-// and code byte; r_P is recovered as d u_P / omega, i.e. the cycle is the exact V-cycle of the
-// operator whose diagonal is d -- symmetric, as CG needs):
-//   PRE : b1[aggregate] = sum over its cells of ((1-omega)/omega) d_P u_P + sum_f c_f u_nb
-//   POST: v = u + P e1;  z_P = (1-omega) v_P + u_P + (omega/d_P) sum_f c_f v_nb;  partial r.z
-// P e1 is never materialised: a 2x2 cell block of a thread is one aggregate in xy, so the thread adds
-// its own aggregate's correction and those of the four in-plane neighbour aggregates (and of the
-// aggregate below/above) to the staged neighbour values on the fly.
+// voxel-grid (level 0) passes.  The CG update kernel leaves
+//     u = r / d     (FP32, pitched rows, one halo plane below and above;  d = a_P rounded to FP32)
+// next to the FP64 residual; the cycle is the exact V-cycle of the operator whose diagonal is d
+// (r_P is recovered as d u_P where needed) -- symmetric, as CG needs.  The passes are 7-point stencils
+// with the same tiling as k_stencil_tma: a CTA marches a 64x16 xy tile in z, planes of the input field
+// (u or an iterate, both pitched FP32 with halo planes) arrive by TMA in a shared-memory ring,
+// zero-filled outside the domain, so a face towards the outside multiplies a zero and needs no
+// boundary logic.  1/d and d come from a table indexed by position class and code byte.
+//   OUT 0: restrict pass -> u of level 1         OUT 1: sweep pass -> pitched iterate
+//   OUT 2: last sweep -> z (FP32, unpitched) and the partial r.z
+//   ADD_E: the input is  sc * stored + e1 of the cell's aggregate.  P e1 is never materialised: the
+//          2x2 cell block of a thread is one aggregate in xy, so the thread adds its own aggregate's
+//          correction and those of the four in-plane neighbour aggregates (and of the aggregate
+//          below/above) to the staged values on the fly.
+//   IN_IS_U: the staged field is u itself (otherwise my cells' u is read from global memory).
 // ------------------------------------------------------------------------------------------------
 // the staged box starts 4 cells left of the tile: a TMA box must start on a 16-byte boundary of the row
 constexpr int MG_NST = 6, MG_BOXW = TX + 8, MG_HX = 4;
@@ -294,12 +325,13 @@ constexpr int MG_STAGE_BYTES = MG_BOXW * BOXH * 4;
 constexpr int MG_STAGE_STRIDE = (MG_STAGE_BYTES + 127) / 128 * 128;
 
 struct MgFine {
-  const float* e1;  // level-1 correction (POST)
-  float* b1;        // level-1 right-hand side (PRE)
+  const float* e1;     // level-1 correction (ADD_E)
+  float* u1;           // level-1 scaled right-hand side (OUT 0)
+  const float* dinv1;  // level-1 1/a_P (nullptr: level 1 is the dense level, store the plain sum)
   int nx1, ny1, nz1;
-  int fy, fz;       // y / z coarsened (x always is: nx even >= 4)
-  int lo, hi;       // z-slabs: halo planes of u / e1 hold the lower / upper neighbour's values
-  float omega;
+  int fy, fz;          // y / z coarsened (x always is: nx even >= 4)
+  int lo, hi;          // z-slabs: halo planes of the fields / e1 hold the lower / upper neighbour's values
+  int pitch;           // floats per row of the pitched fields
 };
 
 // position class of a cell along one axis: 0 interior, 1 first, 2 last
@@ -313,25 +345,26 @@ __device__ __forceinline__ float mg_diag32(const Coef& C, int cls, unsigned c, b
 
 __device__ __forceinline__ float pickf(bool c, float a, float b) { return c ? a : b; }
 
-// the three per-solve tables over (position class, code byte): [0] omega/d, [1] d (1-omega)/omega
+// the two per-solve tables over (position class, code byte): [0] 1/d, [1] d
 constexpr int MG_TAB = 27 * 128;
-__global__ void k_mg_tables(float* __restrict__ t, const Coef C, int flat, float omega) {
+__global__ void k_mg_tables(float* __restrict__ t, const Coef C, int flat) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= MG_TAB) return;
   const float d = mg_diag32(C, e >> 7, (unsigned)(e & 127), flat != 0);
-  t[e] = omega / d;
-  t[MG_TAB + e] = d * ((1.f - omega) / omega);
+  t[e] = 1.f / d;
+  t[MG_TAB + e] = d;
 }
 
-template <int POST>
+template <int OUT, int ADD_E, int IN_IS_U>
 __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUtensorMap tm,
                                                      const uint8_t* __restrict__ code, const float* __restrict__ gtab,
-                                                     float* __restrict__ zout,
-                                                     const MgFine M, const Coef C, const Dom D, const Plan P,
+                                                     const float* __restrict__ uown, float* __restrict__ fout,
+                                                     float* __restrict__ zout, const MgFine M, const MgPass K,
+                                                     const Coef C, const Dom D, const Plan P,
                                                      const Scal* __restrict__ S, double* __restrict__ partials) {
   __shared__ __align__(128) unsigned char tiles[MG_NST * MG_STAGE_STRIDE];
   __shared__ __align__(8) uint64_t full[MG_NST];
-  __shared__ float tab[27 * 128];  // PRE: d (1-omega)/omega   POST: omega / d
+  __shared__ float tab[27 * 128];  // OUT 0: d    otherwise: 1/d
   __shared__ double red[32 * 3];
   if (S->done) return;
   const int tid = threadIdx.x, lx = (tid & 31) * 2, ly = (tid >> 5) * 2;
@@ -339,12 +372,12 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     for (int s = 0; s < MG_NST; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
-  const float om1 = 1.f - M.omega;
-  for (int e = tid; e < MG_TAB; e += NTHR) tab[e] = gtab[(POST ? 0 : MG_TAB) + e];
+  for (int e = tid; e < MG_TAB; e += NTHR) tab[e] = gtab[(OUT == 0 ? MG_TAB : 0) + e];
   uint32_t seq = 0;
   double acc[3] = {0, 0, 0};
-  const long plane = (long)D.nx * D.ny;
+  const long plane = (long)D.nx * D.ny, pplane = (long)M.pitch * D.ny;
   const int coff = (ly + 1) * MG_BOXW + lx + MG_HX;
+  const float sc = K.sc, as = K.a * K.sc, gs = K.g * K.sc;
   const float sx0 = (float)C.same[0][0], sx1 = (float)C.same[0][1], sy0 = (float)C.same[1][0];
   const float sy1 = (float)C.same[1][1], sz0 = (float)C.same[2][0], sz1 = (float)C.same[2][1];
   const float dfx = (float)C.diff[0], dfy = (float)C.diff[1], dfz = (float)C.diff[2];
@@ -360,10 +393,10 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     const int ya = 3 * mg_cls(gy, D.ny), yc = 3 * mg_cls(gy + 1, D.ny);
     const int xa = mg_cls(gx, D.nx), xb = mg_cls(gx + 1, D.nx);
     const int ta = (ya + xa) << 7, tb = (ya + xb) << 7, tc = (yc + xa) << 7, td = (yc + xb) << 7;
-    // aggregate of my block and its in-plane neighbours (POST)
+    // aggregate of my block and its in-plane neighbours
     const int X = gx >> 1, Y = M.fy ? gy >> 1 : gy;
-    const bool hW = POST && row0 && X > 0, hE = POST && row0 && X + 1 < M.nx1;
-    const bool hN = POST && row0 && Y > 0, hS = POST && row0 && Y + 1 < M.ny1;
+    const bool hW = ADD_E && row0 && X > 0, hE = ADD_E && row0 && X + 1 < M.nx1;
+    const bool hN = ADD_E && row0 && Y > 0, hS = ADD_E && row0 && Y + 1 < M.ny1;
     const long eoff = (long)Y * M.nx1 + X;
     const long eplane = (long)M.nx1 * M.ny1;
 
@@ -376,23 +409,29 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
         tma_load_3d(tiles + st * MG_STAGE_STRIDE, &tm, &full[st], xo - MG_HX, yo - 1, zb + k);
       }
     }
-    long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of cell a in plane zb
+    long ci = ((long)zb * D.ny + gy) * D.nx + gx;    // global index of cell a in plane zb
+    long cu = ((long)zb * D.ny + gy) * M.pitch + gx;  // the same cell in a pitched field
     unsigned cn0 = row0 ? *reinterpret_cast<const unsigned short*>(code + ci) : 0u;
     unsigned cn1 = row1 ? *reinterpret_cast<const unsigned short*>(code + ci + D.nx) : 0u;
-    // corrections of my aggregate column: E[0] own, E[1..4] W,E,N,S neighbours; Ez of the pair below / above
-    float E0 = 0.f, EW = 0.f, EE = 0.f, EN = 0.f, ES = 0.f, Eprev = 0.f, Enext = 0.f;
-    float nE0 = 0.f, nEW = 0.f, nEE = 0.f, nEN = 0.f, nES = 0.f;  // prefetched for the next aggregate plane
-    auto load_E = [&](int Z, float& a0, float& aw, float& ae, float& an, float& as) {
-      a0 = aw = ae = an = as = 0.f;
+    float2 un0 = make_float2(0.f, 0.f), un1 = make_float2(0.f, 0.f);  // u of my cells (when the staged field is an iterate)
+    if (!IN_IS_U) {
+      if (row0) un0 = *reinterpret_cast<const float2*>(uown + cu);
+      if (row1) un1 = *reinterpret_cast<const float2*>(uown + cu + M.pitch);
+    }
+    // corrections of my aggregate column: own, W,E,N,S neighbours; of the aggregate plane below; prefetched next
+    float E0 = 0.f, EW = 0.f, EE = 0.f, EN = 0.f, ES = 0.f, Eprev = 0.f;
+    float nE0 = 0.f, nEW = 0.f, nEE = 0.f, nEN = 0.f, nES = 0.f;
+    auto load_E = [&](int Z, float& a0, float& aw, float& ae, float& an, float& as_) {
+      a0 = aw = ae = an = as_ = 0.f;
       if ((Z < 0 && !(M.lo && Z == -1)) || (Z >= M.nz1 && !(M.hi && Z == M.nz1))) return;
       const float* ep = M.e1 + (long)Z * eplane + eoff;
       if (row0) a0 = ep[0];
       if (hW) aw = ep[-1];
       if (hE) ae = ep[1];
       if (hN) an = ep[-M.nx1];
-      if (hS) as = ep[M.nx1];
+      if (hS) as_ = ep[M.nx1];
     };
-    if (POST) {
+    if (ADD_E) {
       const int Z = M.fz ? zb >> 1 : zb;
       float d1, d2, d3, d4;
       load_E(Z - 1, Eprev, d1, d2, d3, d4);
@@ -426,24 +465,28 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
         mbar_expect_tx(&full[st], MG_STAGE_BYTES);
         tma_load_3d(tiles + st * MG_STAGE_STRIDE, &tm, &full[st], xo - MG_HX, yo - 1, zb + k - 1 + MG_NST);
       }
-      const uint32_t sc = (seq + k) % MG_NST, sn = (seq + k + 1) % MG_NST;
+      const uint32_t scs = (seq + k) % MG_NST, sn = (seq + k + 1) % MG_NST;
       mbar_wait(&full[sn], ((seq + k + 1) / MG_NST) & 1);
-      const float* cur = reinterpret_cast<const float*>(tiles + sc * MG_STAGE_STRIDE) + coff;
+      const float* cur = reinterpret_cast<const float*>(tiles + scs * MG_STAGE_STRIDE) + coff;
       const float* nxt = reinterpret_cast<const float*>(tiles + sn * MG_STAGE_STRIDE) + coff;
       const float2 nt0 = *reinterpret_cast<const float2*>(nxt), nb0 = *reinterpret_cast<const float2*>(nxt + MG_BOXW);
       float2 ut = nt0, ub = nb0;
       const unsigned k0 = cn0, k1 = cn1;
+      const float2 u0 = IN_IS_U ? pt : un0, u1 = IN_IS_U ? pb : un1;  // u of my cells
       if (k < len) {
         if (row0) cn0 = *reinterpret_cast<const unsigned short*>(code + ci + plane);
         if (row1) cn1 = *reinterpret_cast<const unsigned short*>(code + ci + plane + D.nx);
+        if (!IN_IS_U) {
+          if (row0) un0 = *reinterpret_cast<const float2*>(uown + cu + pplane);
+          if (row1) un1 = *reinterpret_cast<const float2*>(uown + cu + pplane + M.pitch);
+        }
       }
       float2 pn = *reinterpret_cast<const float2*>(cur - MG_BOXW);
       float2 ps = *reinterpret_cast<const float2*>(cur + 2 * MG_BOXW);
       float pwt = cur[-1], pet = cur[2], pwb = cur[MG_BOXW - 1], peb = cur[MG_BOXW + 2];
-      const float2 ct = pt, cb2 = pb;  // u of my own cells (before the correction is added)
+      const float2 ct = pt, cb2 = pb;  // stored values of my own cells
       float2 bt = lt, bb = lb;         // plane below
-      float e0 = 0.f;
-      if (POST) {
+      if (ADD_E) {
         // corrections: a new aggregate plane starts at every plane (z not coarsened) or at even planes
         const bool first_of_pair = !M.fz || !(lz & 1);
         if (first_of_pair) {
@@ -454,13 +497,13 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
         const bool has_lo = D.z0 + lz > 0, has_hi = D.z0 + lz < D.nzg - 1;
         const float Eb = !has_lo ? 0.f : ((M.fz && (lz & 1)) ? E0 : Eprev);
         const float Ea = !has_hi ? 0.f : ((M.fz && !(lz & 1) && lz + 1 < D.nz) ? E0 : nE0);
-        e0 = E0;
         const float e0c = row1 ? E0 : 0.f;
-        pt.x += e0; pt.y += e0; pb.x += e0c; pb.y += e0c;
-        pwt += EW; pwb += EW; pet += EE; peb += EE;
-        pn.x += EN; pn.y += EN; ps.x += ES; ps.y += ES;
-        bt.x += Eb; bt.y += Eb; bb.x += Eb; bb.y += Eb;
-        ut.x += Ea; ut.y += Ea; ub.x += Ea; ub.y += Ea;
+        // in = sc * stored + e;  cells outside the domain (stored 0, e 0) stay 0
+        pt.x = fmaf(sc, pt.x, E0); pt.y = fmaf(sc, pt.y, E0); pb.x = fmaf(sc, pb.x, e0c); pb.y = fmaf(sc, pb.y, e0c);
+        pwt = fmaf(sc, pwt, EW); pwb = fmaf(sc, pwb, EW); pet = fmaf(sc, pet, EE); peb = fmaf(sc, peb, EE);
+        pn.x = fmaf(sc, pn.x, EN); pn.y = fmaf(sc, pn.y, EN); ps.x = fmaf(sc, ps.x, ES); ps.y = fmaf(sc, ps.y, ES);
+        bt.x = fmaf(sc, bt.x, Eb); bt.y = fmaf(sc, bt.y, Eb); bb.x = fmaf(sc, bb.x, Eb); bb.y = fmaf(sc, bb.y, Eb);
+        ut.x = fmaf(sc, ut.x, Ea); ut.y = fmaf(sc, ut.y, Ea); ub.x = fmaf(sc, ub.x, Ea); ub.y = fmaf(sc, ub.y, Ea);
       }
       const unsigned ca = k0 & 0xffu, cb = k0 >> 8, cc = k1 & 0xffu, cd = k1 >> 8;
       const bool ha = ca & C_PH, hb = cb & C_PH, hc = cc & C_PH, hd = cd & C_PH;
@@ -500,27 +543,37 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
 
       const float* tz = tab + 9 * 128 * mg_cls(D.z0 + lz, D.nzg);
       const float wa = tz[ta | (ca & 127u)], wb = tz[tb | (cb & 127u)], wc = tz[tc | (cc & 127u)], wd = tz[td | (cd & 127u)];
-      if (!POST) {
+      // local part a in_P + b u_P and the neighbour sum scaled by g (times sc when the inputs were not rescaled above)
+      const float ka = ADD_E ? K.a : as, kg = ADD_E ? K.g : gs;
+      const float la = ka * pt.x + K.b * u0.x, lb2 = ka * pt.y + K.b * u0.y;
+      const float lc = ka * pb.x + K.b * u1.x, ld = ka * pb.y + K.b * u1.y;
+      if (OUT == 0) {
+        // res = d (a in + b u) + g sum
         float s = 0.f;
-        if (row0) s += (wa * ct.x + qa) + (wb * ct.y + qb);
-        if (row1) s += (wc * cb2.x + qc) + (wd * cb2.y + qd);
-        if (M.fz) {
-          sacc = (lz & 1) ? sacc + s : s;
-          if (row0 && ((lz & 1) || lz == D.nz - 1)) M.b1[(long)(lz >> 1) * ((long)M.nx1 * M.ny1) + (long)Y * M.nx1 + X] = sacc;
-        } else if (row0) {
-          M.b1[(long)lz * ((long)M.nx1 * M.ny1) + (long)Y * M.nx1 + X] = s;
+        if (row0) s += (wa * la + kg * qa) + (wb * lb2 + kg * qb);
+        if (row1) s += (wc * lc + kg * qc) + (wd * ld + kg * qd);
+        const bool last = !M.fz || (lz & 1) || lz == D.nz - 1;
+        sacc = (M.fz && (lz & 1)) ? sacc + s : s;
+        if (row0 && last) {
+          const long ic = (long)(M.fz ? lz >> 1 : lz) * eplane + eoff;
+          M.u1[ic] = M.dinv1 ? sacc * M.dinv1[ic] : sacc;
         }
       } else {
-        // z = (1-omega) v_P + u_P + (omega/d) sum;  r_P = d u_P / omega
-        if (row0) {
-          const float za = om1 * pt.x + ct.x + wa * qa, zb2 = om1 * pt.y + ct.y + wb * qb;
-          *reinterpret_cast<float2*>(zout + ci) = make_float2(za, zb2);
-          acc[0] += (double)(__fdividef(ct.x, wa) * za) + (double)(__fdividef(ct.y, wb) * zb2);
-        }
-        if (row1) {
-          const float zc2 = om1 * pb.x + cb2.x + wc * qc, zd = om1 * pb.y + cb2.y + wd * qd;
-          *reinterpret_cast<float2*>(zout + ci + D.nx) = make_float2(zc2, zd);
-          acc[0] += (double)(__fdividef(cb2.x, wc) * zc2) + (double)(__fdividef(cb2.y, wd) * zd);
+        // out = a in + b u + g (1/d) sum
+        const float za = la + kg * wa * qa, zb2 = lb2 + kg * wb * qb, zc2 = lc + kg * wc * qc, zd = ld + kg * wd * qd;
+        if (OUT == 1) {
+          if (row0) *reinterpret_cast<float2*>(fout + cu) = make_float2(za, zb2);
+          if (row1) *reinterpret_cast<float2*>(fout + cu + M.pitch) = make_float2(zc2, zd);
+        } else {
+          // r_P = d u_P
+          if (row0) {
+            *reinterpret_cast<float2*>(zout + ci) = make_float2(za, zb2);
+            acc[0] += (double)(__fdividef(u0.x, wa) * za) + (double)(__fdividef(u0.y, wb) * zb2);
+          }
+          if (row1) {
+            *reinterpret_cast<float2*>(zout + ci + D.nx) = make_float2(zc2, zd);
+            acc[0] += (double)(__fdividef(u1.x, wc) * zc2) + (double)(__fdividef(u1.y, wd) * zd);
+          }
         }
       }
       lt = ct;
@@ -528,10 +581,11 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
       pt = nt0;
       pb = nb0;
       ci += plane;
+      cu += pplane;
     }
     seq += nplanes;
   }
-  if (POST) {
+  if (OUT == 2) {
     block_sum<3>(acc, red);
     if (tid == 0) {
       partials[blockIdx.x * 3 + 0] = acc[0];
@@ -543,8 +597,8 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
 
 // ------------------------------------------------------------------------------------------------
 // CG vector kernels of the multigrid-preconditioned iteration.  Rows round-robin over a fixed grid.
-//   k_cg_update_mg: x += alpha p;  r -= alpha q;  u = omega r / d (FP32);  partial r.r     (53 B per cell)
-//   k_mg_make_u   : u = omega r / d alone (after the initial residual, and for the test hook)
+//   k_cg_update_mg<1>: x += alpha p;  r -= alpha q;  u = r / d (FP32);  partial r.r       (53 B per cell)
+//   k_cg_update_mg<0>: u = r / d alone (after the initial residual, and for the test hook)
 //   k_cg_dir_mg   : p = z + beta p   (first = 1: p = z; z is FP32)                          (20 B per cell)
 // u rows are `pitch` floats apart (multiple of 4: a TMA row stride must be a multiple of 16 bytes);
 // u points at plane 0 of a field with one halo plane below.
@@ -557,7 +611,7 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ x, do
                                                       const Scal* __restrict__ S, int par,
                                                       double* __restrict__ partials) {
   __shared__ double red[32 * 2];
-  __shared__ float tab[27 * 128];  // omega / d
+  __shared__ float tab[27 * 128];  // 1 / d
   if (S->done) return;
   for (int e = threadIdx.x; e < MG_TAB; e += blockDim.x) tab[e] = gtab[e];
   __syncthreads();

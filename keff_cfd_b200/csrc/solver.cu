@@ -257,11 +257,12 @@ struct Mg {
   int z0[MG_MAX_LEVELS] = {0}, nzg[MG_MAX_LEVELS] = {0};  // per level: first global plane of my slab, global planes
   bool dist = false, lo = false, hi = false;              // z-slab mode; a neighbour below / above
   MgLevel G{};                 // the dense level gathered over all ranks (== L[nlev] on one GPU)
-  CUtensorMap tm_u;
-  int pitch = 0;               // floats per row of u
+  CUtensorMap tm_u, tm_x[2];   // u and the two iterate fields of the voxel grid
+  int pitch = 0;               // floats per row of those fields
   Plan plan{};
   int grid = 0, gu = 0;        // CTAs of the stencil passes / of the row-wise vector kernels
-  float omega = 0.9f;
+  int nu = 2;                  // smoothing sweeps before and after the coarse correction
+  float om[4] = {0.595f, 1.614f, 0.f, 0.f};  // their weights (Chebyshev points of [0.4, 1.9] for nu = 2)
   Dom D{};
   Coef C{};
 };
@@ -291,6 +292,16 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   Ctx& c = ctx();
   mg.D = D;
   mg.C = C;
+  if (const char* e = getenv("KEFFB200_MG_OMEGA")) {  // "w1,w2,..": overrides the smoothing weights (experiments)
+    int k = 0;
+    for (const char* q = e; *q && k < 4; k++) {
+      char* end = nullptr;
+      mg.om[k] = strtof(q, &end);
+      if (end == q) break;
+      q = *end == ',' ? end + 1 : end;
+    }
+    if (k >= 1) mg.nu = k;
+  }
   Nccl& nc = c.nccl;
   mg.dist = c.dist_active && nc.world > 1;
   mg.lo = mg.dist && D.z0 > 0;
@@ -338,7 +349,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
     }
     mg.z0[l] = z0;
     mg.nzg[l] = nzg;
-    if (l > 0) floats += 7 * (((size_t)nx * ny * (nz + 2) + 31) / 32 * 32);
+    if (l > 0) floats += 9 * (((size_t)nx * ny * (nz + 2) + 31) / 32 * 32);
     if (l > 0 && (long)nx * ny * nzg <= MG_DENSE_MAX) break;
     if (!L.fx && !L.fy && !L.fz) return 0;  // cannot get down to a dense level (only with odd slabs)
     if (l + 1 >= MG_MAX_LEVELS) return fail(KEFFB200_EINVAL, "multigrid hierarchy too deep");
@@ -371,15 +382,15 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   }
   if (!c.mg_inv) KB_CUDA(cudaMalloc(&c.mg_inv, (size_t)MG_DENSE_MAX * MG_DENSE_MAX * sizeof(double)));
   if (!c.mg_tab) KB_CUDA(cudaMalloc(&c.mg_tab, (size_t)2 * MG_TAB * sizeof(float)));
-  k_mg_tables<<<(MG_TAB + 255) / 256, 256, 0, c.st>>>(c.mg_tab, C, D.nzg == 1, mg.omega);
+  k_mg_tables<<<(MG_TAB + 255) / 256, 256, 0, c.st>>>(c.mg_tab, C, D.nzg == 1);
   KB_LAUNCHED();
   KB_CUDA(cudaMemsetAsync(c.mg_pool, 0, floats * sizeof(float), c.st));
   float* base = c.mg_pool;
   for (int k = 1; k <= mg.nlev; k++) {
     MgLevel& L = mg.L[k];
     const size_t plane = (size_t)L.nx * L.ny, stride = (plane * (L.nz + 2) + 31) / 32 * 32;
-    float** arr[7] = {&L.cx, &L.cy, &L.cz, &L.wsum, &L.dinv, &L.b, &L.e};
-    for (int a = 0; a < 7; a++) {
+    float** arr[9] = {&L.cx, &L.cy, &L.cz, &L.wsum, &L.dinv, &L.u, &L.e, &L.t0, &L.t1};
+    for (int a = 0; a < 9; a++) {
       *arr[a] = base + plane;  // plane 0 (one spare plane below)
       base += stride;
     }
@@ -387,7 +398,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   mg.G = mg.L[mg.nlev];
   if (mg.dist) {
     mg.G.nz = mg.nzg[mg.nlev];
-    float** arr[6] = {&mg.G.cx, &mg.G.cy, &mg.G.cz, &mg.G.wsum, &mg.G.b, &mg.G.e};
+    float** arr[6] = {&mg.G.cx, &mg.G.cy, &mg.G.cz, &mg.G.wsum, &mg.G.u, &mg.G.e};
     for (int a = 0; a < 6; a++) {
       *arr[a] = base;
       base += MG_DENSE_MAX;
@@ -424,23 +435,43 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.G, c.mg_inv);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
-  // voxel-grid passes: tensor map on u, work plan (z chunks of even length so aggregates stay whole)
+  // voxel-grid passes: tensor maps on u and the iterate fields, work plan (z chunks of even length so
+  // aggregates stay whole)
   mg.pitch = mg_pitch(D.nx);
   {
-    const size_t uplane = (size_t)mg.pitch * D.ny;
-    KB_CUDA(cudaMemsetAsync(c.u, 0, uplane * sizeof(float), c.st));
-    KB_CUDA(cudaMemsetAsync(c.u + uplane * (D.nz + 1), 0, uplane * sizeof(float), c.st));
-    cuuint64_t dims[3] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nz + 2};
-    cuuint64_t strides[2] = {(cuuint64_t)mg.pitch * 4, (cuuint64_t)uplane * 4};
-    cuuint32_t box[3] = {MG_BOXW, BOXH, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult rc = c.encode(&mg.tm_u, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.u, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return fail(KEFFB200_ECUDA, "cuTensorMapEncodeTiled (u) failed (%d)", (int)rc);
+    const size_t uplane = (size_t)mg.pitch * D.ny, need = uplane * (D.nz + 2);
+    if (mg.nu >= 2 && need > c.cap_xf) {
+      for (int k = 0; k < 2; k++) {
+        if (c.xf[k]) cudaFree(c.xf[k]);
+        c.xf[k] = nullptr;
+      }
+      c.cap_xf = 0;
+      for (int k = 0; k < 2; k++) KB_CUDA(cudaMalloc(&c.xf[k], need * sizeof(float)));
+      c.cap_xf = need;
+    }
+    float* fields[3] = {c.u, mg.nu >= 2 ? c.xf[0] : nullptr, mg.nu >= 2 ? c.xf[1] : nullptr};
+    CUtensorMap* maps[3] = {&mg.tm_u, &mg.tm_x[0], &mg.tm_x[1]};
+    for (int k = 0; k < 3; k++) {
+      if (!fields[k]) continue;
+      // the halo planes stay zero at the global ends; the row padding of the iterates is never written
+      if (k == 0) {
+        KB_CUDA(cudaMemsetAsync(fields[k], 0, uplane * sizeof(float), c.st));
+        KB_CUDA(cudaMemsetAsync(fields[k] + uplane * (D.nz + 1), 0, uplane * sizeof(float), c.st));
+      } else {
+        KB_CUDA(cudaMemsetAsync(fields[k], 0, need * sizeof(float), c.st));
+      }
+      cuuint64_t dims[3] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nz + 2};
+      cuuint64_t strides[2] = {(cuuint64_t)mg.pitch * 4, (cuuint64_t)uplane * 4};
+      cuuint32_t box[3] = {MG_BOXW, BOXH, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult rc = c.encode(maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fields[k], dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) return fail(KEFFB200_ECUDA, "cuTensorMapEncodeTiled (multigrid field) failed (%d)", (int)rc);
+    }
   }
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_fine<1>, NTHR, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_fine<2, 1, 1>, NTHR, 0);
   occ = std::max(occ, 1);
   {
     const long rows = (long)D.ny * D.nz;
@@ -475,7 +506,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   return 0;
 }
 
-// u = omega r / d from a residual that some other kernel produced
+// u = r / d from a residual that some other kernel produced
 static int mg_make_u(const Mg& mg, double* r) {
   Ctx& c = ctx();
   const int vt = vec_threads(mg.D.nx, 2);
@@ -485,30 +516,87 @@ static int mg_make_u(const Mg& mg, double* r) {
   return 0;
 }
 
-// z = M r, r given through u = omega r / d (ctx().u); partial r.z lands in ctx().partials, stride 3.
-// z-slabs: every pass that reads a neighbour plane is preceded by the exchange of that array's halo planes.
-static int mg_vcycle(const Mg& mg, float* z) {
+// One pass over the voxel grid.  in: 0 = u, 1/2 = iterate field 0/1;  out: -1 restrict, -2 z, 0/1 iterate field.
+static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass& K, float* z) {
   Ctx& c = ctx();
-  const float om = mg.omega;
-  const int lo = mg.lo, hi = mg.hi;
   const MgLevel& L0 = mg.L[0];
   const MgLevel& L1 = mg.L[1];
-  MgFine mf{L1.e, L1.b, L1.nx, L1.ny, L1.nz, L0.fy, L0.fz, lo, hi, mg.omega};
-  KB_TRY(exchange_planes(c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
-  k_mg_fine<0><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
-  KB_LAUNCHED();
-  for (int k = 1; k < mg.nlev; k++) {
-    const MgLevel& L = mg.L[k];
-    const MgLevel& N = mg.L[k + 1];
-    KB_TRY(exchange_planes(L.b, (size_t)L.nx * L.ny * sizeof(float), L.nz, c.st));
-    k_mg_pre<<<mg_row_grid(N.nx, N.ny, N.nz), 256, 0, c.st>>>(mg_view(L), L.b, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
-                                                               N.b, om, lo, hi, mg_bx(N.nx), c.S);
-    KB_LAUNCHED();
+  const size_t uplane = (size_t)mg.pitch * mg.D.ny;
+  MgFine mf{L1.e, L1.u, mg.nlev > 1 ? L1.dinv : nullptr, L1.nx, L1.ny, L1.nz, L0.fy, L0.fz, mg.lo, mg.hi, mg.pitch};
+  const CUtensorMap& tm = in == 0 ? mg.tm_u : mg.tm_x[in - 1];
+  const float* uown = c.u + uplane;
+  float* fout = out >= 0 ? c.xf[out] + uplane : nullptr;
+#define KB_FINE(O, E, U) \
+  k_mg_fine<O, E, U><<<mg.grid, NTHR, 0, c.st>>>(tm, c.code, c.mg_tab, uown, fout, z, mf, K, mg.C, mg.D, mg.plan, c.S, c.partials)
+  const bool isu = in == 0;
+  if (out == -1) {
+    if (isu) KB_FINE(0, 0, 1); else KB_FINE(0, 0, 0);
+  } else if (out == -2) {
+    if (add_e) { if (isu) KB_FINE(2, 1, 1); else KB_FINE(2, 1, 0); }
+    else KB_FINE(2, 0, 0);
+  } else {
+    if (add_e) KB_FINE(1, 1, 0);
+    else if (isu) KB_FINE(1, 0, 1);
+    else KB_FINE(1, 0, 0);
   }
+#undef KB_FINE
+  KB_LAUNCHED();
+  if (out >= 0) KB_TRY(exchange_planes(c.xf[out] + uplane, uplane * sizeof(float), mg.D.nz, c.st));
+  return 0;
+}
+
+// z = M r, r given through u = r / d (ctx().u); partial r.z lands in ctx().partials, stride 3.
+// Per level: nu-1 sweeps (the first iterate w_1 u is implicit), the restrict pass, ... coarse solve ...,
+// the sweep that adds the correction, nu-1 more sweeps (weights in reverse order).
+// z-slabs: every array that a pass reads across a slab boundary has its halo planes exchanged first.
+static int mg_vcycle(const Mg& mg, float* z) {
+  Ctx& c = ctx();
+  const int lo = mg.lo, hi = mg.hi, nu = mg.nu;
+  const float* w = mg.om;
+  KB_TRY(exchange_planes(c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
+  // ---- voxel grid, down ----
+  int cur = 0;  // field holding the current iterate (0 = u, scaled by w_1)
+  float sc = w[0];
+  for (int k = 1; k < nu; k++) {
+    const int out = cur == 1 ? 1 : 0;  // iterate fields alternate: u -> x0 -> x1 -> x0 ..
+    KB_TRY(mg_fine_pass(mg, cur, out, false, MgPass{sc, 1.f - w[k], w[k], w[k]}, z));
+    cur = out + 1;
+    sc = 1.f;
+  }
+  KB_TRY(mg_fine_pass(mg, cur, -1, false, MgPass{sc, -1.f, 1.f, 1.f}, z));
+  const int fine_cur = cur;
+  const float fine_sc = sc;
+  // ---- stored levels, down ----
+  const float* lcur[MG_MAX_LEVELS];
+  float lsc[MG_MAX_LEVELS];
+  for (int l = 1; l < mg.nlev; l++) {
+    const MgLevel& L = mg.L[l];
+    const MgLevel& N = mg.L[l + 1];
+    const size_t pb = (size_t)L.nx * L.ny * sizeof(float);
+    const dim3 gl = mg_row_grid(L.nx, L.ny, L.nz), gn = mg_row_grid(N.nx, N.ny, N.nz);
+    KB_TRY(exchange_planes(L.u, pb, L.nz, c.st));
+    const float* in = L.u;
+    float s1 = w[0];
+    for (int k = 1; k < nu; k++) {
+      float* out = in == L.t0 ? L.t1 : L.t0;
+      k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, MgPass{s1, 1.f - w[k], w[k], w[k]}, L.fx, L.fy, L.fz,
+                                          N.nx, N.ny, out, lo, hi, mg_bx(L.nx), c.S);
+      KB_LAUNCHED();
+      KB_TRY(exchange_planes(out, pb, L.nz, c.st));
+      in = out;
+      s1 = 1.f;
+    }
+    k_mg_restrict<<<gn, 256, 0, c.st>>>(mg_view(L), in, L.u, MgPass{s1, -1.f, 1.f, 1.f}, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
+                                        N.u, l + 1 < mg.nlev ? N.dinv : nullptr, lo, hi, mg_bx(N.nx), c.S);
+    KB_LAUNCHED();
+    lcur[l] = in;
+    lsc[l] = s1;
+  }
+  // ---- dense level (its u array holds the plain right-hand side) ----
   {
     const MgLevel& L = mg.L[mg.nlev];
-    if (mg.dist) KB_TRY(allgather_f32(L.b, mg.G.b, (size_t)L.nx * L.ny * L.nz));
-    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, mg.G.b, mg.G.e, mg.ndense, c.S);
+    if (mg.dist) KB_TRY(allgather_f32(L.u, mg.G.u, (size_t)L.nx * L.ny * L.nz));
+    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, mg.G.u, mg.G.e, mg.ndense, c.S);
     KB_LAUNCHED();
     if (mg.dist) {  // my planes of the global correction, plus one plane either side where it exists
       const size_t plane = (size_t)L.nx * L.ny;
@@ -517,16 +605,38 @@ static int mg_vcycle(const Mg& mg, float* z) {
                               (size_t)(b - a) * plane * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
     }
   }
-  for (int k = mg.nlev - 1; k >= 1; k--) {
-    const MgLevel& L = mg.L[k];
-    const MgLevel& N = mg.L[k + 1];
-    k_mg_post<<<mg_row_grid(L.nx, L.ny, L.nz), 256, 0, c.st>>>(mg_view(L), L.b, N.e, L.fx, L.fy, L.fz, N.nx, N.ny,
-                                                                L.e, om, lo, hi, mg_bx(L.nx), c.S);
-    KB_LAUNCHED();
-    KB_TRY(exchange_planes(L.e, (size_t)L.nx * L.ny * sizeof(float), L.nz, c.st));
+  // ---- stored levels, up ----
+  for (int l = mg.nlev - 1; l >= 1; l--) {
+    const MgLevel& L = mg.L[l];
+    const MgLevel& N = mg.L[l + 1];
+    const size_t pb = (size_t)L.nx * L.ny * sizeof(float);
+    const dim3 gl = mg_row_grid(L.nx, L.ny, L.nz);
+    const float* in = lcur[l];
+    float s1 = lsc[l];
+    for (int k = nu - 1; k >= 0; k--) {
+      float* out = k == 0 ? L.e : (in == L.t0 ? L.t1 : L.t0);
+      const MgPass K{s1, 1.f - w[k], w[k], w[k]};
+      if (k == nu - 1)
+        k_mg_sweep<1><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, N.e, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, lo, hi,
+                                            mg_bx(L.nx), c.S);
+      else
+        k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, lo, hi,
+                                            mg_bx(L.nx), c.S);
+      KB_LAUNCHED();
+      KB_TRY(exchange_planes(out, pb, L.nz, c.st));
+      in = out;
+      s1 = 1.f;
+    }
   }
-  k_mg_fine<1><<<mg.grid, NTHR, 0, c.st>>>(mg.tm_u, c.code, c.mg_tab, z, mf, mg.C, mg.D, mg.plan, c.S, c.partials);
-  KB_LAUNCHED();
+  // ---- voxel grid, up ----
+  cur = fine_cur;
+  sc = fine_sc;
+  for (int k = nu - 1; k >= 0; k--) {
+    const int out = k == 0 ? -2 : (cur == 1 ? 1 : 0);
+    KB_TRY(mg_fine_pass(mg, cur, out, k == nu - 1, MgPass{sc, 1.f - w[k], w[k], w[k]}, z));
+    cur = out + 1;
+    sc = 1.f;
+  }
   KB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -572,7 +682,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   if (mg_eligible(D, P.flags)) KB_TRY(mg_setup(mg, D, C));
   const long n2 = (long)(n / 2);
   const int gm = mg_grid(n2);
-  const long check_every = mg.on ? std::min<long>(P.check_every, 4) : P.check_every;
+  const long check_every = mg.on ? std::min<long>(P.check_every, 2) : P.check_every;
 
   Scal h0;
   memset(&h0, 0, sizeof h0);
@@ -814,6 +924,11 @@ void keffb200_shutdown(void) {
   if (c.u) cudaFree(c.u);
   c.u = nullptr;
   c.cap_u = 0;
+  for (int k = 0; k < 2; k++) {
+    if (c.xf[k]) cudaFree(c.xf[k]);
+    c.xf[k] = nullptr;
+  }
+  c.cap_xf = 0;
   if (c.mg_pool) cudaFree(c.mg_pool);
   if (c.mg_inv) cudaFree(c.mg_inv);
   if (c.mg_tab) cudaFree(c.mg_tab);
