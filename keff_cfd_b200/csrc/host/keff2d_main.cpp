@@ -3,7 +3,12 @@
 // T-/Q-maps; the numerical path is libkeffb200 (C ABI).  Modes as in Keff2D/keff2D.cpp:
 //   single image (:69-192), mesh-convergence sweep (:193-332), batch %05d.jpg (:333-485).
 // Usage: keff2D [input.txt] [--check-inputs]   (--check-inputs: parse + decode only, no GPU)
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "host_common.hpp"
 
@@ -27,31 +32,75 @@ int main(int argc, char** argv) {
 
   if (o.BatchFlag == 1 && o.MeshFlag == 0) {
     // ---- batch: %05d.jpg, img = 0 .. NumImages-1 (keff2D.cpp:341-360) ----
-    std::vector<uint8_t> all;
+    // The reference decodes and solves image by image inside an OpenMP loop (NumCores threads).  Here
+    // NumCores threads only decode (JPEG -> structure bytes, straight into one staging array); the
+    // images are handed to the GPU in chunks, so chunk k is being solved while chunk k+1 is decoded.
+    if (o.NumImg < 1) { fprintf(stderr, "keff2D: NumImages must be >= 1 in batch mode\n"); return 1; }
+    GrayImage first;
+    if (!load_jpeg_gray("00000.jpg", first)) { fprintf(stderr, "keff2D: 00000.jpg: %s\n", first.err.c_str()); return 1; }
+    const int nx = first.w * o.MeshIncreaseX, ny = first.h * o.MeshIncreaseY;
+    const size_t cells = (size_t)nx * ny;
+    std::vector<uint8_t> all(cells * o.NumImg);
     std::vector<double> poro(o.NumImg);
-    int nx = 0, ny = 0;
-    for (int img = 0; img < o.NumImg; img++) {
-      char name[64];
-      snprintf(name, sizeof name, "%05d.jpg", img);
-      GrayImage g;
-      if (!load_jpeg_gray(name, g)) { fprintf(stderr, "keff2D: %s: %s\n", name, g.err.c_str()); return 1; }
-      if (g.channels != 1) fprintf(stderr, "keff2D: warning: %s has %d channels, using luminance\n", name, g.channels);
-      std::vector<uint8_t> s;
-      structure_from_image(g, o.MeshIncreaseX, o.MeshIncreaseY, s, poro[img]);
-      if (img == 0) { nx = g.w * o.MeshIncreaseX; ny = g.h * o.MeshIncreaseY; }
-      if (g.w * o.MeshIncreaseX != nx || g.h * o.MeshIncreaseY != ny) {
-        fprintf(stderr, "keff2D: %s: all batch images must have the same size\n", name);
-        return 1;
-      }
-      all.insert(all.end(), s.begin(), s.end());
-    }
-    if (check_only) { printf("batch ok: %d images %dx%d\n", o.NumImg, nx, ny); return 0; }
-    if (keffb200_init(0)) return die("init");
     std::vector<keffb200_result> res(o.NumImg);
     std::vector<double> T;
-    if (o.printTmap) T.resize(all.size());
-    if (keffb200_solve2d_batch(all.data(), o.NumImg, nx, ny, &p, o.printTmap ? T.data() : nullptr, res.data()))
-      return die("solve2d_batch");
+    if (o.printTmap && !check_only) T.resize(all.size());
+    const int chunk = std::max(1, std::min(o.NumImg, 2048));
+    const int nchunks = (o.NumImg + chunk - 1) / chunk;
+    std::vector<std::atomic<int>> left(nchunks);  // images of the chunk still being decoded
+    for (int k = 0; k < nchunks; k++) left[k] = std::min(chunk, o.NumImg - k * chunk);
+    std::atomic<int> next{0};
+    std::atomic<bool> failed{false};
+    std::mutex mu;
+    std::condition_variable cv;
+    std::string first_error;
+    auto decode = [&]() {
+      for (int img = next++; img < o.NumImg && !failed; img = next++) {
+        char name[64];
+        snprintf(name, sizeof name, "%05d.jpg", img);
+        GrayImage g;
+        std::string e;
+        if (!load_jpeg_gray(name, g)) e = std::string(name) + ": " + g.err;
+        else if (g.w * o.MeshIncreaseX != nx || g.h * o.MeshIncreaseY != ny) e = std::string(name) + ": all batch images must have the same size";
+        if (!e.empty()) {
+          std::lock_guard<std::mutex> lk(mu);
+          if (first_error.empty()) first_error = e;
+          failed = true;
+          cv.notify_all();
+          return;
+        }
+        if (g.channels != 1) fprintf(stderr, "keff2D: warning: %s has %d channels, using luminance\n", name, g.channels);
+        std::vector<uint8_t> sl;
+        structure_from_image(g, o.MeshIncreaseX, o.MeshIncreaseY, sl, poro[img]);
+        memcpy(all.data() + cells * img, sl.data(), cells);
+        if (--left[img / chunk] == 0) {
+          std::lock_guard<std::mutex> lk(mu);
+          cv.notify_all();
+        }
+      }
+    };
+    const int nthreads = std::max(1, std::min(o.numCores, o.NumImg));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(decode);
+    int rc = 0;
+    if (!check_only && keffb200_init(0)) rc = die("init");
+    for (int k = 0; k < nchunks && rc == 0; k++) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || left[k] == 0; });
+      }
+      if (failed) break;
+      if (check_only) continue;
+      const int i0 = k * chunk, cnt = std::min(chunk, o.NumImg - i0);
+      if (keffb200_solve2d_batch(all.data() + cells * i0, cnt, nx, ny, &p, o.printTmap ? T.data() + cells * i0 : nullptr,
+                                 res.data() + i0))
+        rc = die("solve2d_batch");
+    }
+    if (rc != 0) failed = true;
+    for (auto& th : pool) th.join();
+    if (!first_error.empty()) { fprintf(stderr, "keff2D: %s\n", first_error.c_str()); return 1; }
+    if (rc != 0) return rc;
+    if (check_only) { printf("batch ok: %d images %dx%d\n", o.NumImg, nx, ny); return 0; }
     const double per = since(t0) / o.NumImg;
     for (int img = 0; img < o.NumImg; img++) {
       char name[64];
@@ -59,10 +108,10 @@ int main(int argc, char** argv) {
       append_row(o, false, res[img].keff, res[img].q_left, res[img].q_right, res[img].iters, name, nx * ny, poro[img], per, 1);
       if (o.printTmap) {
         snprintf(name, sizeof name, "TMAP_%05d.csv", img);
-        write_tmap(name, T.data() + (size_t)img * nx * ny, nx, ny, 1, false);
+        write_tmap(name, T.data() + cells * img, nx, ny, 1, false);
       }
     }
-    if (o.verbose) printf("Done, saving output\n");
+    if (o.verbose) printf("Done, saving output (%d images, %d decode threads, %.3f s)\n", o.NumImg, nthreads, since(t0));
     keffb200_shutdown();
     return 0;
   }

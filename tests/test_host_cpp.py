@@ -146,3 +146,19 @@ def test_keff2d_batch_and_keff3d_programs(built, tmp_path, R):
     assert len(row) == 17 and abs(float(row[0]) - want) / want < 1e-5 and row[5] == "vol.csv" and row[6] == "1728"
     t = open(os.path.join(d, "T3.csv")).read().splitlines()
     assert t[0] == "x,y,z,T" and len(t) == 1 + 1728
+
+
+def test_batch_decode_pipeline_on_cpu(built, tmp_path):
+    """Batch mode decodes %05d.jpg on NumCores threads in chunks; --check-inputs runs
+    that whole pipeline without a GPU.  A missing image must fail the run with its name."""
+    from PIL import Image
+    from keff_cfd_b200 import structures as S
+    d = str(tmp_path)
+    for i in range(37):
+        Image.fromarray(S.to_gray(S.disc_image(i, n=32))).save(os.path.join(d, "%05d.jpg" % i), quality=95)
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=2, name="x.jpg", tmap=0, batch=1, nimg=37))
+    r = subprocess.run([os.path.join(built, "keff2D"), "input.txt", "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0 and "batch ok: 37 images 64x64" in r.stdout, (r.stdout, r.stderr)
+    os.remove(os.path.join(d, "00020.jpg"))
+    r = subprocess.run([os.path.join(built, "keff2D"), "input.txt", "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "00020.jpg" in r.stderr
