@@ -31,6 +31,7 @@ namespace kb {
 
 constexpr int MG_MAX_LEVELS = 24;
 constexpr int MG_DENSE_MAX = 64;
+constexpr long MG_REPLICATE_CELLS = 1L << 18;  // z-slabs: levels of at most this many cells are replicated
 
 // one stored (coarse) level; every array has one spare plane below plane 0 and one above plane nz-1
 struct MgLevel {

@@ -256,7 +256,8 @@ struct Mg {
   int ndense = 0;              // cells of the dense level (global)
   int z0[MG_MAX_LEVELS] = {0}, nzg[MG_MAX_LEVELS] = {0};  // per level: first global plane of my slab, global planes
   bool dist = false, lo = false, hi = false;              // z-slab mode; a neighbour below / above
-  MgLevel G{};                 // the dense level gathered over all ranks (== L[nlev] on one GPU)
+  int la = 1 << 20;            // z-slabs: levels >= la are replicated on every rank (global extent, no exchanges)
+  int nzl_la = 0, z0_la = 0;   // my planes of level la (its u is written / its e is read through this slice)
   CUtensorMap tm_u, tm_x[2];   // u and the two iterate fields of the voxel grid
   int pitch = 0;               // floats per row of those fields
   Plan plan{};
@@ -329,12 +330,24 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   int nx = D.nx, ny = D.ny, nz = D.nz, nzg = D.nzg, z0 = D.z0, l = 0, zdone = 0;
   double hx = 1.0 / nx, hy = 1.0 / ny, hz = 1.0 / nzg;
   size_t floats = 0;
+  bool rep = false;  // this level is replicated
+  mg.la = 1 << 20;
   while (true) {
     MgLevel& L = mg.L[l];
+    // z-slabs: once a level is small its halo exchanges cost more than its arithmetic, so from there on every
+    // rank holds the whole level (the level above all-gathers its restricted residual into it)
+    if (mg.dist && !rep && l > 0 && (long)nx * ny * nzg <= MG_REPLICATE_CELLS) {
+      rep = true;
+      mg.la = l;
+      mg.nzl_la = nz;
+      mg.z0_la = z0;
+      nz = nzg;
+      z0 = 0;
+    }
     L.nx = nx;
     L.ny = ny;
     L.nz = nz;
-    const bool cx = nx > 1, cy = ny > 1, cz = mg.dist ? (zdone < kz && nz > 1) : nz > 1;
+    const bool cx = nx > 1, cy = ny > 1, cz = (mg.dist && !rep) ? (zdone < kz && nz > 1) : nz > 1;
     double hmin = 1e300;
     if (cx) hmin = std::min(hmin, hx);
     if (cy) hmin = std::min(hmin, hy);
@@ -372,7 +385,6 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   }
   mg.nlev = l;
   mg.ndense = mg.L[l].nx * mg.L[l].ny * nzg;
-  floats += 6 * MG_DENSE_MAX;  // gathered dense level
   if (floats > c.cap_mg) {
     if (c.mg_pool) cudaFree(c.mg_pool);
     c.mg_pool = nullptr;
@@ -395,44 +407,38 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       base += stride;
     }
   }
-  mg.G = mg.L[mg.nlev];
-  if (mg.dist) {
-    mg.G.nz = mg.nzg[mg.nlev];
-    float** arr[6] = {&mg.G.cx, &mg.G.cy, &mg.G.cz, &mg.G.wsum, &mg.G.u, &mg.G.e};
-    for (int a = 0; a < 6; a++) {
-      *arr[a] = base;
-      base += MG_DENSE_MAX;
-    }
-    mg.G.dinv = nullptr;
-  }
-  // operators
-  {
-    const MgLevel& L0 = mg.L[0];
-    MgLevel& L1 = mg.L[1];
-    k_mg_coarsen_fine<<<mg_grid((long)L1.nx * L1.ny * L1.nz), 256, 0, c.st>>>(c.code, C, D, L0.fx, L0.fy, L0.fz, L1);
-    KB_LAUNCHED();
-  }
+  // operators.  Level k is built from level k-1; where level k is the first replicated one, every rank builds
+  // its own planes inside the global arrays and the planes of the others arrive by in-place all-gathers.
   for (int k = 1; k <= mg.nlev; k++) {
     MgLevel& L = mg.L[k];
-    if (k > 1) {
-      k_mg_coarsen_level<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(mg.L[k - 1], L);
-      KB_LAUNCHED();
+    const bool rep_k = k >= mg.la, first_rep = k == mg.la;
+    const size_t plane = (size_t)L.nx * L.ny, pb = plane * sizeof(float);
+    MgLevel T = L;  // target of the coarsening kernel: my slice when this is the first replicated level
+    if (first_rep) {
+      T.nz = mg.nzl_la;
+      const size_t off = (size_t)mg.z0_la * plane;
+      T.cx += off;
+      T.cy += off;
+      T.cz += off;
+      T.wsum += off;
     }
-    const size_t pb = (size_t)L.nx * L.ny * sizeof(float);
-    KB_TRY(exchange_planes(L.cz, pb, L.nz, c.st));  // cz[-1]: the face towards the lower neighbour
-    k_mg_dinv<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(L, mg.lo);
+    const int gk = mg_grid((long)T.nx * T.ny * T.nz);
+    if (k == 1) k_mg_coarsen_fine<<<gk, 256, 0, c.st>>>(c.code, C, D, mg.L[0].fx, mg.L[0].fy, mg.L[0].fz, T);
+    else k_mg_coarsen_level<<<gk, 256, 0, c.st>>>(mg.L[k - 1], T);
     KB_LAUNCHED();
-    KB_TRY(exchange_planes(L.dinv, pb, L.nz, c.st));
+    if (first_rep) {
+      const size_t cnt = plane * mg.nzl_la;
+      KB_TRY(allgather_f32(T.cx, L.cx, cnt));
+      KB_TRY(allgather_f32(T.cy, L.cy, cnt));
+      KB_TRY(allgather_f32(T.cz, L.cz, cnt));
+      KB_TRY(allgather_f32(T.wsum, L.wsum, cnt));
+    }
+    if (!rep_k) KB_TRY(exchange_planes(L.cz, pb, L.nz, c.st));  // cz[-1]: the face towards the lower neighbour
+    k_mg_dinv<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(L, rep_k ? 0 : (int)mg.lo);
+    KB_LAUNCHED();
+    if (!rep_k) KB_TRY(exchange_planes(L.dinv, pb, L.nz, c.st));
   }
-  if (mg.dist) {
-    const MgLevel& L = mg.L[mg.nlev];
-    const size_t cnt = (size_t)L.nx * L.ny * L.nz;
-    KB_TRY(allgather_f32(L.cx, mg.G.cx, cnt));
-    KB_TRY(allgather_f32(L.cy, mg.G.cy, cnt));
-    KB_TRY(allgather_f32(L.cz, mg.G.cz, cnt));
-    KB_TRY(allgather_f32(L.wsum, mg.G.wsum, cnt));
-  }
-  k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.G, c.mg_inv);
+  k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.L[mg.nlev], c.mg_inv);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
   // voxel-grid passes: tensor maps on u and the iterate fields, work plan (z chunks of even length so
@@ -522,7 +528,10 @@ static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass&
   const MgLevel& L0 = mg.L[0];
   const MgLevel& L1 = mg.L[1];
   const size_t uplane = (size_t)mg.pitch * mg.D.ny;
-  MgFine mf{L1.e, L1.u, mg.nlev > 1 ? L1.dinv : nullptr, L1.nx, L1.ny, L1.nz, L0.fy, L0.fz, mg.lo, mg.hi, mg.pitch};
+  // level 1 replicated: my planes are a slice of its global arrays (the planes either side are the neighbours')
+  const size_t o1 = mg.la == 1 ? (size_t)mg.z0_la * L1.nx * L1.ny : 0;
+  MgFine mf{L1.e + o1, L1.u + o1, mg.nlev > 1 ? L1.dinv + o1 : nullptr, L1.nx, L1.ny, mg.la == 1 ? mg.nzl_la : L1.nz,
+            L0.fy, L0.fz, mg.lo, mg.hi, mg.pitch};
   const CUtensorMap& tm = in == 0 ? mg.tm_u : mg.tm_x[in - 1];
   const float* uown = c.u + uplane;
   float* fout = out >= 0 ? c.xf[out] + uplane : nullptr;
@@ -567,49 +576,58 @@ static int mg_vcycle(const Mg& mg, float* z) {
   const int fine_cur = cur;
   const float fine_sc = sc;
   // ---- stored levels, down ----
+  // gather_u(l): level l is the first replicated one and its u was just restricted into my slice of it
+  auto gather_u = [&](int l) -> int {
+    if (l != mg.la) return 0;
+    const MgLevel& L = mg.L[l];
+    const size_t plane = (size_t)L.nx * L.ny;
+    return allgather_f32(L.u + (size_t)mg.z0_la * plane, L.u, plane * mg.nzl_la);
+  };
+  KB_TRY(gather_u(1));
   const float* lcur[MG_MAX_LEVELS];
   float lsc[MG_MAX_LEVELS];
   for (int l = 1; l < mg.nlev; l++) {
     const MgLevel& L = mg.L[l];
     const MgLevel& N = mg.L[l + 1];
+    const bool rep = l >= mg.la, nslice = l + 1 == mg.la;  // nslice: I fill only my planes of the next level
+    const int llo = rep ? 0 : lo, lhi = rep ? 0 : hi;
     const size_t pb = (size_t)L.nx * L.ny * sizeof(float);
-    const dim3 gl = mg_row_grid(L.nx, L.ny, L.nz), gn = mg_row_grid(N.nx, N.ny, N.nz);
-    KB_TRY(exchange_planes(L.u, pb, L.nz, c.st));
+    const size_t on = nslice ? (size_t)mg.z0_la * N.nx * N.ny : 0;
+    const int nnz = nslice ? mg.nzl_la : N.nz;
+    const dim3 gl = mg_row_grid(L.nx, L.ny, L.nz), gn = mg_row_grid(N.nx, N.ny, nnz);
+    if (!rep) KB_TRY(exchange_planes(L.u, pb, L.nz, c.st));
     const float* in = L.u;
     float s1 = w[0];
     for (int k = 1; k < nu; k++) {
       float* out = in == L.t0 ? L.t1 : L.t0;
       k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, MgPass{s1, 1.f - w[k], w[k], w[k]}, L.fx, L.fy, L.fz,
-                                          N.nx, N.ny, out, lo, hi, mg_bx(L.nx), c.S);
+                                          N.nx, N.ny, out, llo, lhi, mg_bx(L.nx), c.S);
       KB_LAUNCHED();
-      KB_TRY(exchange_planes(out, pb, L.nz, c.st));
+      if (!rep) KB_TRY(exchange_planes(out, pb, L.nz, c.st));
       in = out;
       s1 = 1.f;
     }
-    k_mg_restrict<<<gn, 256, 0, c.st>>>(mg_view(L), in, L.u, MgPass{s1, -1.f, 1.f, 1.f}, L.fx, L.fy, L.fz, N.nx, N.ny, N.nz,
-                                        N.u, l + 1 < mg.nlev ? N.dinv : nullptr, lo, hi, mg_bx(N.nx), c.S);
+    k_mg_restrict<<<gn, 256, 0, c.st>>>(mg_view(L), in, L.u, MgPass{s1, -1.f, 1.f, 1.f}, L.fx, L.fy, L.fz, N.nx, N.ny, nnz,
+                                        N.u + on, l + 1 < mg.nlev ? N.dinv + on : nullptr, llo, lhi, mg_bx(N.nx), c.S);
     KB_LAUNCHED();
+    KB_TRY(gather_u(l + 1));
     lcur[l] = in;
     lsc[l] = s1;
   }
-  // ---- dense level (its u array holds the plain right-hand side) ----
+  // ---- dense level (replicated; its u array holds the plain right-hand side) ----
   {
     const MgLevel& L = mg.L[mg.nlev];
-    if (mg.dist) KB_TRY(allgather_f32(L.u, mg.G.u, (size_t)L.nx * L.ny * L.nz));
-    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, mg.G.u, mg.G.e, mg.ndense, c.S);
+    k_mg_dense_apply<<<1, MG_DENSE_MAX, 0, c.st>>>(c.mg_inv, L.u, L.e, mg.ndense, c.S);
     KB_LAUNCHED();
-    if (mg.dist) {  // my planes of the global correction, plus one plane either side where it exists
-      const size_t plane = (size_t)L.nx * L.ny;
-      const int z0 = mg.z0[mg.nlev], a = std::max(z0 - 1, 0), b = std::min(z0 + L.nz + 1, mg.nzg[mg.nlev]);
-      KB_CUDA(cudaMemcpyAsync(L.e + (ptrdiff_t)(a - z0) * (ptrdiff_t)plane, mg.G.e + (size_t)a * plane,
-                              (size_t)(b - a) * plane * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
-    }
   }
   // ---- stored levels, up ----
   for (int l = mg.nlev - 1; l >= 1; l--) {
     const MgLevel& L = mg.L[l];
     const MgLevel& N = mg.L[l + 1];
+    const bool rep = l >= mg.la, nslice = l + 1 == mg.la;
+    const int llo = rep ? 0 : lo, lhi = rep ? 0 : hi;
     const size_t pb = (size_t)L.nx * L.ny * sizeof(float);
+    const size_t on = nslice ? (size_t)mg.z0_la * N.nx * N.ny : 0;  // my planes of the replicated level below
     const dim3 gl = mg_row_grid(L.nx, L.ny, L.nz);
     const float* in = lcur[l];
     float s1 = lsc[l];
@@ -617,13 +635,13 @@ static int mg_vcycle(const Mg& mg, float* z) {
       float* out = k == 0 ? L.e : (in == L.t0 ? L.t1 : L.t0);
       const MgPass K{s1, 1.f - w[k], w[k], w[k]};
       if (k == nu - 1)
-        k_mg_sweep<1><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, N.e, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, lo, hi,
+        k_mg_sweep<1><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, N.e + on, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, llo, lhi,
                                             mg_bx(L.nx), c.S);
       else
-        k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, lo, hi,
+        k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, llo, lhi,
                                             mg_bx(L.nx), c.S);
       KB_LAUNCHED();
-      KB_TRY(exchange_planes(out, pb, L.nz, c.st));
+      if (!rep) KB_TRY(exchange_planes(out, pb, L.nz, c.st));
       in = out;
       s1 = 1.f;
     }
