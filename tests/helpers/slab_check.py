@@ -1,0 +1,34 @@
+"""torchrun --nproc-per-node N scratch/slab_check.py [n]: z-slab solve vs single-GPU solve."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np, torch, torch.distributed as dist
+import keff_cfd_b200 as K
+from keff_cfd_b200 import api, dist as D
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+nzg = int(sys.argv[2]) if len(sys.argv) > 2 else n
+D.init_comm(rank, world, local)
+z0, nzl = D.slab_extent(nzg, rank, world)
+loc = api.bernoulli_volume_dev((nzl, n, n), 0.5, 1234, z0=z0, device=local)
+halo = D.exchange_structure_halos(loc, rank, world)
+p = api.default_params()
+torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+r = D.solve3d_slab(halo, z0, nzg, p, want_T=(n <= 128))
+torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+if rank == 0:
+    print(f"slab {n}x{n}x{nzg} over {world} ranks:", {k: r[k] for k in ("keff", "q_left", "q_right", "rel_residual", "iters", "status", "gpu_ms")}, f"wall {dt:.3f}s")
+if n <= 128:
+    parts = [torch.empty_like(r["T"]) for _ in range(world)] if nzg % world == 0 else None
+    if parts is not None:
+        dist.all_gather(parts, r["T"])
+        if rank == 0:
+            Tfull = torch.cat(parts).cpu().numpy()
+            full = api.bernoulli_volume_dev((nzg, n, n), 0.5, 1234, device=local)
+            # single-GPU solve needs world==1 semantics: use a fresh params and the non-slab entry point
+            s = api.solve3d(full, p, device=local)
+            print("single:", s["keff"], s["iters"], "| keff rel diff", abs(s["keff"] - r["keff"]) / s["keff"],
+                  "| T maxdiff", float(np.abs(s["T"].cpu().numpy() - Tfull).max()))
+dist.barrier()
+dist.destroy_process_group()
