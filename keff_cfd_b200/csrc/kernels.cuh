@@ -13,39 +13,45 @@ namespace kb {
 // Keff3D/keff3D.cpp:105-120) and the harmonic-mean selection inside DiscretizeMatrixCD2D/3D.
 // m points at local plane 0; planes -1 and nz are readable when lo/hi are set (slab neighbours).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_make_code(const uint8_t* __restrict__ m, uint8_t* __restrict__ code, Dom D, int lo, int hi) {
-  const long plane = (long)D.nx * D.ny, n = plane * D.nz;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % D.nx);
-    const long t = i / D.nx;
-    const int y = (int)(t % D.ny), z = (int)(t / D.ny);
-    const unsigned me = m[i] == 1;
-    unsigned c = me;
-    if (x > 0 && (unsigned)(m[i - 1] == 1) != me) c |= C_W;
-    if (x < D.nx - 1 && (unsigned)(m[i + 1] == 1) != me) c |= C_E;
-    if (y < D.ny - 1 && (unsigned)(m[i + D.nx] == 1) != me) c |= C_S;
-    if (y > 0 && (unsigned)(m[i - D.nx] == 1) != me) c |= C_N;
-    if ((z > 0 || lo) && (unsigned)(m[i - plane] == 1) != me) c |= C_F;
-    if ((z < D.nz - 1 || hi) && (unsigned)(m[i + plane] == 1) != me) c |= C_B;
-    code[i] = (uint8_t)c;
+__global__ void __launch_bounds__(256) k_make_code(const uint8_t* __restrict__ m, uint8_t* __restrict__ code, Dom D, int lo,
+                                                   int hi) {
+  const long plane = (long)D.nx * D.ny;
+  const int rows = D.ny * D.nz;  // rows (y,z) round-robin over the grid: no per-cell division
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % D.ny, z = row / D.ny;
+    const bool hasN = y > 0, hasS = y < D.ny - 1, hasF = z > 0 || lo, hasB = z < D.nz - 1 || hi;
+    const long base = (long)row * D.nx;
+    for (int x = threadIdx.x; x < D.nx; x += blockDim.x) {
+      const long i = base + x;
+      const unsigned me = m[i] == 1;
+      unsigned c = me;
+      if (x > 0 && (unsigned)(m[i - 1] == 1) != me) c |= C_W;
+      if (x < D.nx - 1 && (unsigned)(m[i + 1] == 1) != me) c |= C_E;
+      if (hasS && (unsigned)(m[i + D.nx] == 1) != me) c |= C_S;
+      if (hasN && (unsigned)(m[i - D.nx] == 1) != me) c |= C_N;
+      if (hasF && (unsigned)(m[i - plane] == 1) != me) c |= C_F;
+      if (hasB && (unsigned)(m[i + plane] == 1) != me) c |= C_B;
+      code[i] = (uint8_t)c;
+    }
   }
 }
 
 // Initial field: linear ramp between the wall temperatures evaluated at the cell centres, or the
 // constant TL the reference actually starts from (SolInitLinear, Keff2D/keff2D.h:584-611, whose
 // integer division collapses the ramp).
-__global__ void k_init_field(double* __restrict__ T, Dom D, double tl, double tr, int constant) {
-  const long n = (long)D.nx * D.ny * D.nz;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % D.nx);
-    T[i] = constant ? tl : tl + (tr - tl) * ((x + 0.5) / D.nx);
+__global__ void __launch_bounds__(256) k_init_field(double* __restrict__ T, Dom D, double tl, double tr, int constant) {
+  const int rows = D.ny * D.nz;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    double* Tr = T + (long)row * D.nx;
+    for (int x = threadIdx.x; x < D.nx; x += blockDim.x) Tr[x] = constant ? tl : tl + (tr - tl) * ((x + 0.5) / D.nx);
   }
 }
 
-enum { MODE_APPLY = 0, MODE_INIT = 1, MODE_RESID = 2 };
+enum { MODE_APPLY = 0, MODE_INIT = 1, MODE_RESID = 2, MODE_INIT_R = 3 };
 // MODE_APPLY: o0 = A*in,              partials {in.A in, -, -}
 // MODE_INIT : o0 = r = b - A*in, o1 = p = r/a_P, partials {r.z, r.r, b.b}
 // MODE_RESID: no output,              partials {-, r.r, sum|r|}
+// MODE_INIT_R: o0 = r = b - A*in,       partials {-, r.r, b.b}   (the multigrid path builds its own z)
 
 template <int MODE>
 __device__ __forceinline__ void cell_epilogue(const Coef& C, unsigned c, bool x0, bool x1, const Faces& F,
@@ -61,6 +67,10 @@ __device__ __forceinline__ void cell_epilogue(const Coef& C, unsigned c, bool x0
       out0 = r;
       out1 = z;
       acc[0] += r * z;
+      acc[1] += r * r;
+      acc[2] += b * b;
+    } else if (MODE == MODE_INIT_R) {
+      out0 = r;
       acc[1] += r * r;
       acc[2] += b * b;
     } else {

@@ -60,14 +60,14 @@ struct MgLevelView {
 // hierarchy construction
 // ------------------------------------------------------------------------------------------------
 // level 1 from the code bytes of the voxel grid (fine dims in D, global z end decided from D.nzg)
-__global__ void k_mg_coarsen_fine(const uint8_t* __restrict__ code, const Coef C, const Dom D, int fx, int fy, int fz,
-                                  MgLevel L) {
-  const long n1 = (long)L.nx * L.ny * L.nz;
+__global__ void __launch_bounds__(256) k_mg_coarsen_fine(const uint8_t* __restrict__ code, const Coef C, const Dom D, int fx,
+                                                         int fy, int fz, MgLevel L, int bx) {
   const float sx = fx ? 0.5f : 1.0f, sy = fy ? 0.5f : 1.0f, sz = fz ? 0.5f : 1.0f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n1; i += (long)gridDim.x * blockDim.x) {
-    const int X = (int)(i % L.nx);
-    const long t = i / L.nx;
-    const int Y = (int)(t % L.ny), Z = (int)(t / L.ny);
+  const int tx = threadIdx.x & (bx - 1), trow = threadIdx.x / bx, rpb = blockDim.x / bx;  // bx: power of two
+  for (int Z = blockIdx.y; Z < L.nz; Z += gridDim.y)
+  for (int Y = blockIdx.x * rpb + trow; Y < L.ny; Y += gridDim.x * rpb)
+  for (int X = tx; X < L.nx; X += bx) {
+    const long i = ((long)Z * L.ny + Y) * L.nx + X;
     double ax = 0, ay = 0, az = 0, aw = 0;
     for (int dz = 0; dz <= fz; dz++) {
       const int z = fz ? 2 * Z + dz : Z;
@@ -597,16 +597,20 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------
-// CG vector kernels of the multigrid-preconditioned iteration.  Rows round-robin over a fixed grid.
-//   k_cg_update_mg<1>: x += alpha p;  r -= alpha q;  u = r / d (FP32);  partial r.r       (53 B per cell)
+// CG vector kernels of the multigrid-preconditioned iteration.
+//   k_cg_update_mg<1>: r -= alpha q;  u = r / d (FP32);  partial r.r                       (29 B per cell)
 //   k_cg_update_mg<0>: u = r / d alone (after the initial residual, and for the test hook)
-//   k_cg_dir_mg   : p = z + beta p   (first = 1: p = z; z is FP32)                          (20 B per cell)
+//   k_cg_dir_mg      : x += alpha p;  p = z + beta p  (z is FP32; first = 1: p = z only)     (36 B per cell)
+// x += alpha p rides with the direction update because that kernel reads p anyway (p is then read
+// once per iteration instead of twice).  It must happen exactly once per completed residual update
+// even though every kernel of the blindly enqueued iterations after convergence returns early: the
+// host passes the iteration's index `kit` and the update is applied iff S->it == kit + 1, i.e. iff
+// this iteration's k_step_mg_rr counted it.
 // u rows are `pitch` floats apart (multiple of 4: a TMA row stride must be a multiple of 16 bytes);
 // u points at plane 0 of a field with one halo plane below.
 // ------------------------------------------------------------------------------------------------
 template <int UPDATE>
-__global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ x, double* __restrict__ r,
-                                                      const double* __restrict__ p, const double* __restrict__ q,
+__global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ r, const double* __restrict__ q,
                                                       const uint8_t* __restrict__ code, const float* __restrict__ gtab,
                                                       float* __restrict__ u, int pitch, const Dom D,
                                                       const Scal* __restrict__ S, int par,
@@ -628,14 +632,10 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ x, do
       const long i = base + xx;
       double2 vr = *reinterpret_cast<const double2*>(r + i);
       if (UPDATE) {
-        double2 vx = *reinterpret_cast<const double2*>(x + i);
-        const double2 vp = *reinterpret_cast<const double2*>(p + i), vq = *reinterpret_cast<const double2*>(q + i);
-        vx.x += alpha * vp.x;
-        vx.y += alpha * vp.y;
+        const double2 vq = *reinterpret_cast<const double2*>(q + i);
         vr.x -= alpha * vq.x;
         vr.y -= alpha * vq.y;
         acc[1] += vr.x * vr.x + vr.y * vr.y;
-        *reinterpret_cast<double2*>(x + i) = vx;
         *reinterpret_cast<double2*>(r + i) = vr;
       }
       const unsigned cc = *reinterpret_cast<const unsigned short*>(code + i);
@@ -652,18 +652,32 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ x, do
   }
 }
 
-__global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ p, const float* __restrict__ z, long n2, long n,
-                                                   const Scal* __restrict__ S, int par, int first) {
-  if (S->done) return;
+__global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, double* __restrict__ p,
+                                                   const float* __restrict__ z, long n2, long n,
+                                                   const Scal* __restrict__ S, int par, long long kit, int first) {
+  const bool upd_x = !first && S->it == kit + 1, upd_p = !S->done;
+  if (!upd_x && !upd_p) return;
+  const double alpha = upd_x ? S->rz[par] / S->pq : 0.0;
   const double beta = first ? 0.0 : S->rz[par ^ 1] / S->rz[par];
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
-    const float2 vz = reinterpret_cast<const float2*>(z)[i];
     double2 vp = reinterpret_cast<double2*>(p)[i];
-    vp.x = (double)vz.x + beta * vp.x;
-    vp.y = (double)vz.y + beta * vp.y;
-    reinterpret_cast<double2*>(p)[i] = vp;
+    if (upd_x) {
+      double2 vx = reinterpret_cast<double2*>(x)[i];
+      vx.x += alpha * vp.x;
+      vx.y += alpha * vp.y;
+      reinterpret_cast<double2*>(x)[i] = vx;
+    }
+    if (upd_p) {
+      const float2 vz = reinterpret_cast<const float2*>(z)[i];
+      vp.x = (double)vz.x + beta * vp.x;
+      vp.y = (double)vz.y + beta * vp.y;
+      reinterpret_cast<double2*>(p)[i] = vp;
+    }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = (double)z[n - 1] + beta * p[n - 1];
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (upd_x) x[n - 1] += alpha * p[n - 1];
+    if (upd_p) p[n - 1] = (double)z[n - 1] + beta * p[n - 1];
+  }
 }
 
 // scalar steps of the multigrid-preconditioned iteration

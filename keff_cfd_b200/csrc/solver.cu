@@ -423,7 +423,9 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       T.wsum += off;
     }
     const int gk = mg_grid((long)T.nx * T.ny * T.nz);
-    if (k == 1) k_mg_coarsen_fine<<<gk, 256, 0, c.st>>>(c.code, C, D, mg.L[0].fx, mg.L[0].fy, mg.L[0].fz, T);
+    if (k == 1)
+      k_mg_coarsen_fine<<<mg_row_grid(T.nx, T.ny, T.nz), 256, 0, c.st>>>(c.code, C, D, mg.L[0].fx, mg.L[0].fy, mg.L[0].fz, T,
+                                                                          mg_bx(T.nx));
     else k_mg_coarsen_level<<<gk, 256, 0, c.st>>>(mg.L[k - 1], T);
     KB_LAUNCHED();
     if (first_rep) {
@@ -516,8 +518,8 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
 static int mg_make_u(const Mg& mg, double* r) {
   Ctx& c = ctx();
   const int vt = vec_threads(mg.D.nx, 2);
-  k_cg_update_mg<0><<<mg.gu, vt, 0, c.st>>>(nullptr, r, nullptr, nullptr, c.code, c.mg_tab, c.u + (size_t)mg.pitch * mg.D.ny,
-                                            mg.pitch, mg.D, c.S, 0, c.partials);
+  k_cg_update_mg<0><<<mg.gu, vt, 0, c.st>>>(r, nullptr, c.code, c.mg_tab, c.u + (size_t)mg.pitch * mg.D.ny, mg.pitch, mg.D,
+                                            c.S, 0, c.partials);
   KB_LAUNCHED();
   return 0;
 }
@@ -665,7 +667,6 @@ static int mg_vcycle(const Mg& mg, float* z) {
 static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_params& P, const double* d_Tinit,
                       double* d_Tout, double* d_qL, double* d_qR, keffb200_result* out) {
   Ctx& c = ctx();
-  Nccl& nc = c.nccl;
   if (D.nx < 2 || D.ny < 1 || D.nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", D.nx, D.ny, D.nz);
   if (P.tr == P.tl) return fail(KEFFB200_EINVAL, "TR == TL: Keff undefined");
   if (!(P.ks > 0) || !(P.kf > 0)) return fail(KEFFB200_EINVAL, "conductivities must be positive");
@@ -717,7 +718,8 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   while (true) {
     if (need_init) {
       KB_TRY(exchange_halo(c.x, D, c.st));
-      KB_TRY(stencil_launch<MODE_INIT>(s, 0, r, p));
+      if (mg.on) KB_TRY(stencil_launch<MODE_INIT_R>(s, 0, r, nullptr));  // the cycle builds z itself
+      else KB_TRY(stencil_launch<MODE_INIT>(s, 0, r, p));
       k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 2, c.S);
       KB_LAUNCHED();
       KB_TRY(allreduce_tmp(c.S->tmp, 3));
@@ -731,7 +733,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
         KB_TRY(allreduce_tmp(c.S->tmp, 1));
         k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, 0);
         KB_LAUNCHED();
-        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(p, c.z, n2, (long)n, c.S, 0, 1);
+        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1);
         KB_LAUNCHED();
       }
       need_init = false;
@@ -746,8 +748,8 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       KB_LAUNCHED();
       KB_TRY(allreduce_tmp(&c.S->pq, 1));
       if (mg.on) {
-        k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(x, r, p, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D,
-                                                  c.S, par, c.partials);
+        k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(r, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D, c.S, par,
+                                                  c.partials);
         KB_LAUNCHED();
         k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.gu, 1, c.S);
         KB_LAUNCHED();
@@ -760,7 +762,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
         KB_TRY(allreduce_tmp(c.S->tmp, 1));
         k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, par ^ 1);
         KB_LAUNCHED();
-        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(p, c.z, n2, (long)n, c.S, par, 0);
+        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0);
         KB_LAUNCHED();
         continue;
       }
