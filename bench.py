@@ -37,6 +37,16 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel, units):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/traffic.json: bytes per unit of work, measured at the bench's own launch size), else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return float(t["dram_bytes_per_unit"]) * units
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one background
     `nvidia-smi -lms 100` process, started before and killed after, as in the profiling recipe)."""
@@ -168,17 +178,36 @@ def main():
     # ---- value: structures resident in HBM ----------------------------------------------------
     for _ in range(args.warmup):
         res = api.solve2d_batch(devm, p)
-    barrier()
+    import ctypes
+
+    def timed(fn):
+        """K steps bracketed by barrier + synchronize; device time from CUDA events recorded on the
+        library's compute stream (keffb200_timer_*), wall time beside it; both max over ranks."""
+        barrier()
+        ms = ctypes.c_float()
+        t0 = time.perf_counter()
+        _lib.check(lib.keffb200_timer_start())
+        for _ in range(args.steps):
+            fn()
+        _lib.check(lib.keffb200_timer_stop(ctypes.byref(ms)))
+        barrier()
+        wall = time.perf_counter() - t0
+        return max_over_ranks(ms.value * 1e-3), max_over_ranks(wall)
+
     l0 = lib.keffb200_launch_count()
     clk = ClockSampler(local)
     clk.start()
-    t0 = time.perf_counter()
     kernel_ms = 0.0
-    for _ in range(args.steps):
-        res = api.solve2d_batch(devm, p)
-        kernel_ms += float(res["gpu_ms"][0])                       # CUDA events on the library's stream
-    barrier()
-    dt = max_over_ranks(time.perf_counter() - t0)
+    out_res = []
+
+    def step_value():
+        nonlocal kernel_ms
+        r = api.solve2d_batch(devm, p)
+        kernel_ms += float(r["gpu_ms"][0])                         # the launch alone (CUDA events inside the call)
+        out_res[:] = [r]
+
+    dt, wall_v = timed(step_value)
+    res = out_res[0]
     clocks = clk.summary()
     launches = lib.keffb200_launch_count() - l0
     value = world * n_img * args.steps / dt
@@ -193,18 +222,17 @@ def main():
     harr = host.numpy()
     for _ in range(min(args.warmup, 2)):
         api.solve2d_batch(harr, p)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res_h = api.solve2d_batch(harr, p)
-    barrier()
-    dt_e = max_over_ranks(time.perf_counter() - t0)
+    out_h = []
+    dt_e, wall_e = timed(lambda: out_h.__setitem__(slice(None), [api.solve2d_batch(harr, p)]))
+    res_h = out_h[0]
     e2e = world * n_img * args.steps / dt_e
     keff_mean = float(res_h["keff"].mean())
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * wall_v / args.steps,
+        "timing": "CUDA events on the library's compute stream around the K steps, max over ranks",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"configs[1]: {n_img} synthetic {NPIX}x{NPIX} binary images per GPU (overlapping discs, "
                                "ks:kf 10:1), TRUE relative residual 1e-8 + flux balance 1e-6, on-chip mixed-precision CG with FP64 "
@@ -213,10 +241,12 @@ def main():
                    "rewrites its CG vectors for each image)", "all_converged": bool(ok),
                    "mean_iters": float(iters.mean()), "mean_keff": keff_mean},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(n_img * cells),
-                "d2h_bytes_per_step": int(n_img * 48)},
+                "d2h_bytes_per_step": int(n_img * 48),
+                "ms_per_step": 1e3 * dt_e / args.steps, "wall_ms_per_step": 1e3 * wall_e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"kernel": "k_batch2d_onchip", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_batch2d_onchip", n_img), "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_launch": 16.0 * updates_per_step,
                      "note": "HBM-equivalent: 16 B x cell-updates / kernel time.  The whole CG state of an image lives in "
                              "one SM's shared memory and registers, so this kernel is issue/shared-memory bound, not "
                              "HBM bound, and the figure may exceed 1 (SURVEY 8d, config-2 caveat); the HBM-bound "
@@ -231,7 +261,9 @@ def main():
         gb = 16.0 * n3 ** 3 / (ms * 1e-3) / 1e9
         out["stencil3d"] = {"workload": "configs[3]: 512^3 random binary volume, ks:kf 10:1", "kernel": "k_stencil_tma",
                             "ms_per_sweep": ms, "gcell_updates_per_s": n3 ** 3 / (ms * 1e-3) / 1e9, "bound": "hbm",
-                            "achieved": gb, "peak": peak, "unit": "GB/s", "frac": gb / peak, "traffic": None}
+                            "achieved": gb, "peak": peak, "unit": "GB/s", "frac": gb / peak,
+                            "algorithmic_bytes_per_launch": 16.0 * n3 ** 3,
+                            "traffic": ncu_traffic("k_stencil_tma_apply", n3 ** 3)}
         api.solve3d(vol, p, want_T=False, device=local)               # first call allocates the workspace
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -243,6 +275,33 @@ def main():
                           "ms_per_iter": r3["gpu_ms"] / max(r3["iters"], 1), "keff": r3["keff"],
                           "rel_residual": r3["rel_residual"], "status": r3["status"]}
         del vol
+
+    if world > 1 and not args.no_3d:
+        # configs[4]-shaped weak scaling of the z-slab solve: 1024 x 1024 x 128 planes per GPU (134 M cells per
+        # GPU, the same as the 512^3 single-GPU case; at 8 GPUs this IS configs[4], the 1024^3 volume)
+        from keff_cfd_b200 import dist as KD
+        del devm
+        torch.cuda.empty_cache()
+        KD.init_comm(rank, world, local)
+        nxs, nzg = 1024, 128 * world
+        z0, nzl = KD.slab_extent(nzg, rank, world)
+        loc = api.bernoulli_volume_dev((nzl, nxs, nxs), 0.5, 1234, z0=z0, device=local)
+        halo = KD.exchange_structure_halos(loc, rank, world)
+        del loc
+        ps = api.default_params()
+        for _ in range(2):                                          # first call allocates the workspace
+            barrier()
+            r3 = KD.solve3d_slab(halo, z0, nzg, ps)
+        ms3 = max_over_ranks(float(r3["gpu_ms"]))
+        if rank == 0:
+            out["slab3d"] = {"workload": f"1024x1024x{nzg} random binary volume in {world} z-slabs of 128 planes "
+                             "(configs[4] at 8 GPUs), ks:kf 10:1, halo planes + scalar all-reduces over NCCL",
+                             "gpu_ms": ms3, "solves_per_s": 1e3 / ms3, "iters": r3["iters"],
+                             "ms_per_iter": ms3 / max(r3["iters"], 1), "keff": r3["keff"],
+                             "rel_residual": r3["rel_residual"], "status": r3["status"],
+                             "gcell_iters_per_s": nxs * nxs * nzg * r3["iters"] / (ms3 * 1e-3) / 1e9,
+                             "scaling": "weak (compare gpu_ms with solve3d.gpu_ms of the 1-GPU line: 512^3, same cells per GPU)"}
+        del halo
 
     if rank == 0 and not args.no_cpu:
         from oracle import refbind

@@ -51,7 +51,7 @@ typedef struct keffb200_params {
                                     mixed-precision kernel is used when nx<=128, nx%4==0, ny<=128, ny%8==0) */
 #define KEFFB200_F_NO_MG 8       /* grid solver: plain diagonally preconditioned CG instead of the
                                     multigrid-preconditioned one (used anyway when nx is odd, the
-                                    grid has fewer than 65 cells, ny < 2, or the volume is z-slabbed) */
+                                    grid has fewer than 65 cells, ny < 2, or z-slabs are unequal) */
 #define KEFFB200_F_ZERO_INIT 2   /* start from T = tl everywhere (the reference's actual T0,
                                     Keff2D/keff2D.h:584-611) instead of the linear ramp */
 
@@ -139,6 +139,12 @@ int keffb200_precond(const uint8_t* solid, int nx, int ny, int nz, const keffb20
  * milliseconds per application, measured with CUDA events on the launching stream. */
 int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, const keffb200_params* p,
                              int reps, float* ms_per_apply);
+
+/* Region timer for benchmarks: CUDA events recorded on the library's compute stream (the stream every
+ * kernel of this library is launched on), so a start/stop pair brackets exactly the device work of the
+ * calls made in between, host-buffer copies included.  stop() waits for its event. */
+int keffb200_timer_start(void);
+int keffb200_timer_stop(float* ms);
 
 /* Synthetic input generator for benchmarks and tests (no reference counterpart): voxel i of the
  * range [first_index, first_index + n) is solid iff splitmix64(seed ^ i) < p * 2^64.  The same rule

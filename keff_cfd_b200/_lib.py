@@ -40,6 +40,7 @@ EXPORTS = [
     "keffb200_solve3d", "keffb200_solve3d_dev", "keffb200_solve2d_batch_dev", "keffb200_comm_id",
     "keffb200_dist_init", "keffb200_dist_shutdown", "keffb200_solve3d_slab_dev", "keffb200_apply",
     "keffb200_flux", "keffb200_bench_apply_dev", "keffb200_gen_bernoulli_dev", "keffb200_precond",
+    "keffb200_timer_start", "keffb200_timer_stop",
 ]
 
 _lib = None
@@ -78,6 +79,7 @@ def lib():
         L.keffb200_precond.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp]
         L.keffb200_bench_apply_dev.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, C.c_int,
                                                C.POINTER(C.c_float)]
+        L.keffb200_timer_stop.argtypes = [C.POINTER(C.c_float)]
         L.keffb200_gen_bernoulli_dev.argtypes = [u8p, C.c_size_t, C.c_ulonglong, C.c_ulonglong, C.c_double]
         _lib = L
     return _lib

@@ -44,7 +44,7 @@ struct Ctx {
   bool ready = false;
   int device = -1, sms = 0;
   cudaStream_t st = nullptr, st2 = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx = nullptr, evy = nullptr, evp[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, evx = nullptr, evy = nullptr, evp[3] = {nullptr, nullptr, nullptr};
   PFN_encodeTiled encode = nullptr;
   long launches = 0;
   std::string err;

@@ -331,6 +331,215 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-specialised TMA stencil kernel (nx a multiple of 16): the same tiling and flux arithmetic as
+// k_stencil_tma, but the plane ring is run by a dedicated producer warp and per-stage full/empty
+// mbarriers instead of one __syncthreads per plane, and the code bytes of a plane arrive by TMA in
+// the same stage as the field box (a second tensor map over the u8 code array; its row stride must be
+// a multiple of 16 bytes, hence nx % 16 == 0).  Consumer warps (8: two tile rows each) only ever
+// wait for "plane k+1 has landed"; a warp that is ahead keeps going until the ring is exhausted, and
+// the ring keeps running across work items.  Stage layout: field box (BOXW x BOXH doubles, padded to
+// 128 B) followed by the TX x TY code bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int WS_NST = 6, WS_THR = NTHR + 32, WS_CODE_BYTES = TX * TY;
+constexpr int WS_STAGE = STAGE_STRIDE + WS_CODE_BYTES;
+constexpr int WS_SMEM = WS_NST * WS_STAGE + 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_THR, 3) k_stencil_ws(const __grid_constant__ CUtensorMap tm,
+                                                          const __grid_constant__ CUtensorMap tmc,
+                                                          double* __restrict__ o0, double* __restrict__ o1,
+                                                          const Coef C, const Dom D, const Plan P,
+                                                          const Scal* __restrict__ S, double* __restrict__ partials) {
+  extern __shared__ unsigned char ws_raw[];
+  __shared__ __align__(8) uint64_t full[WS_NST], empty[WS_NST];
+  __shared__ double red[32 * 3];
+  if (S->done) return;
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < WS_NST; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NTHR / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double acc[3] = {0, 0, 0};
+
+  if (tid >= NTHR) {
+    // ---- producer warp: one lane streams every plane of every item of this CTA through the ring ----
+    if (tid == NTHR) {
+      uint32_t seq = 0;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+        const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
+        const int nplanes = min(D.nz, zb + P.zlen) - zb + 2;
+        for (int k = 0; k < nplanes; k++, seq++) {
+          const uint32_t st = seq % WS_NST, use = seq / WS_NST;
+          if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+          unsigned char* dst = tiles + st * WS_STAGE;
+          mbar_expect_tx(&full[st], STAGE_BYTES + WS_CODE_BYTES);
+          // field tensor z index = local plane + 1 (one halo plane below plane 0); the code array has none
+          tma_load_3d(dst, &tm, &full[st], xo - 2, yo - 1, zb + k);
+          tma_load_3d(dst + STAGE_STRIDE, &tmc, &full[st], xo, yo, zb + k - 1);
+        }
+      }
+    }
+  } else {
+    // ---- consumer warps ----
+    const int lane = tid & 31, lx = lane * 2, ly = (tid >> 5) * 2;
+    uint32_t seq = 0;  // planes consumed so far by this CTA (identical in every consumer thread)
+    const long plane = (long)D.nx * D.ny;
+    const int coff = (ly + 1) * BOXW + lx + 2;  // cell a of my 2x2 block inside a staged plane
+    const int koff = STAGE_STRIDE + ly * TX + lx;  // its code byte
+    const double sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0], sy1 = C.same[1][1];
+    const double sz0 = C.same[2][0], sz1 = C.same[2][1];
+    const double dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
+
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+      const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
+      const int len = min(D.nz, zb + P.zlen) - zb, nplanes = len + 2;
+      const int gx = xo + lx, gy = yo + ly;
+      const bool colv = gx < D.nx;
+      const bool row0 = colv && gy < D.ny, row1 = colv && gy + 1 < D.ny;
+      const bool ax0 = gx == 0, bx1 = gx + 1 == D.nx - 1, yt = gy == 0, yb = gy + 1 == D.ny - 1;
+      const double w0 = ax0 ? C.wall[0] : sx0, w1 = ax0 ? C.wall[1] : sx1;
+      const double e0 = bx1 ? C.wall[0] : sx0, e1 = bx1 ? C.wall[1] : sx1;
+      const double n0 = yt ? 0.0 : sy0, n1 = yt ? 0.0 : sy1;
+      const double s0 = (yb || !row1) ? 0.0 : sy0, s1 = (yb || !row1) ? 0.0 : sy1;
+      const double m0 = row1 ? sy0 : 0.0, m1 = row1 ? sy1 : 0.0;
+
+      long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of cell a in plane zb
+      double2 pt, pb, nt, nb;
+      double ga = 0.0, gb = 0.0, gc = 0.0, gd = 0.0;  // flux into my cells from the plane below
+      {
+        const uint32_t q0 = seq % WS_NST, q1 = (seq + 1) % WS_NST;
+        mbar_wait(&full[q0], (seq / WS_NST) & 1);
+        const double* lo = reinterpret_cast<const double*>(tiles + q0 * WS_STAGE) + coff;
+        const double2 mt = *reinterpret_cast<const double2*>(lo), mb = *reinterpret_cast<const double2*>(lo + BOXW);
+        mbar_wait(&full[q1], ((seq + 1) / WS_NST) & 1);
+        const unsigned char* s1p = tiles + q1 * WS_STAGE;
+        const double* c0 = reinterpret_cast<const double*>(s1p) + coff;
+        pt = *reinterpret_cast<const double2*>(c0);
+        pb = *reinterpret_cast<const double2*>(c0 + BOXW);
+        if (D.z0 + zb != 0) {  // face between plane zb-1 and zb
+          const unsigned cn0 = *reinterpret_cast<const unsigned short*>(s1p + koff);
+          const unsigned cn1 = *reinterpret_cast<const unsigned short*>(s1p + koff + TX);
+          const unsigned ca = cn0 & 0xffu, cb = cn0 >> 8, cc = cn1 & 0xffu, cd = cn1 >> 8;
+          ga = pick(ca & C_F, dfz, pick(ca & C_PH, sz1, sz0)) * (mt.x - pt.x);
+          gb = pick(cb & C_F, dfz, pick(cb & C_PH, sz1, sz0)) * (mt.y - pt.y);
+          gc = pick(cc & C_F, dfz, pick(cc & C_PH, sz1, sz0)) * (mb.x - pb.x);
+          gd = pick(cd & C_F, dfz, pick(cd & C_PH, sz1, sz0)) * (mb.y - pb.y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[q0]);  // the plane below the chunk is not read again
+      }
+
+      for (int k = 1; k <= len; k++) {
+        const int lz = zb + k - 1;
+        const uint32_t sc = (seq + k) % WS_NST, sn = (seq + k + 1) % WS_NST;
+        mbar_wait(&full[sn], ((seq + k + 1) / WS_NST) & 1);
+        const unsigned char* scp = tiles + sc * WS_STAGE;
+        const double* cur = reinterpret_cast<const double*>(scp) + coff;
+        const double* nxt = reinterpret_cast<const double*>(tiles + sn * WS_STAGE) + coff;
+        nt = *reinterpret_cast<const double2*>(nxt);
+        nb = *reinterpret_cast<const double2*>(nxt + BOXW);
+        const unsigned k0 = *reinterpret_cast<const unsigned short*>(scp + koff);
+        const unsigned k1 = *reinterpret_cast<const unsigned short*>(scp + koff + TX);
+        const double2 pn = *reinterpret_cast<const double2*>(cur - BOXW);
+        const double2 ps = *reinterpret_cast<const double2*>(cur + 2 * BOXW);
+        const double pwt = cur[-1], pet = cur[2], pwb = cur[BOXW - 1], peb = cur[BOXW + 2];
+        const unsigned ca = k0 & 0xffu, cb = k0 >> 8, cc = k1 & 0xffu, cd = k1 >> 8;
+        const bool fa = ca & C_PH, fb = cb & C_PH, fc = cc & C_PH, fd = cd & C_PH;
+        double qa = -ga, qb = -gb, qc = -gc, qd = -gd;
+        double g;
+        qa += pick(ca & C_W, dfx, pick(fa, w1, w0)) * (pt.x - pwt);
+        g = pick(ca & C_E, dfx, pick(fa, sx1, sx0)) * (pt.x - pt.y);
+        qa += g;
+        qb -= g;
+        qb += pick(cb & C_E, dfx, pick(fb, e1, e0)) * (pt.y - pet);
+        qc += pick(cc & C_W, dfx, pick(fc, w1, w0)) * (pb.x - pwb);
+        g = pick(cc & C_E, dfx, pick(fc, sx1, sx0)) * (pb.x - pb.y);
+        qc += g;
+        qd -= g;
+        qd += pick(cd & C_E, dfx, pick(fd, e1, e0)) * (pb.y - peb);
+        qa += pick(ca & C_N, dfy, pick(fa, n1, n0)) * (pt.x - pn.x);
+        g = pick(ca & C_S, dfy, pick(fa, m1, m0)) * (pt.x - pb.x);
+        qa += g;
+        qc -= g;
+        qc += pick(cc & C_S, dfy, pick(fc, s1, s0)) * (pb.x - ps.x);
+        qb += pick(cb & C_N, dfy, pick(fb, n1, n0)) * (pt.y - pn.y);
+        g = pick(cb & C_S, dfy, pick(fb, m1, m0)) * (pt.y - pb.y);
+        qb += g;
+        qd -= g;
+        qd += pick(cd & C_S, dfy, pick(fd, s1, s0)) * (pb.y - ps.y);
+        if (D.z0 + lz != D.nzg - 1) {
+          ga = pick(ca & C_B, dfz, pick(fa, sz1, sz0)) * (pt.x - nt.x);
+          gb = pick(cb & C_B, dfz, pick(fb, sz1, sz0)) * (pt.y - nt.y);
+          gc = pick(cc & C_B, dfz, pick(fc, sz1, sz0)) * (pb.x - nb.x);
+          gd = pick(cd & C_B, dfz, pick(fd, sz1, sz0)) * (pb.y - nb.y);
+          qa += ga;
+          qb += gb;
+          qc += gc;
+          qd += gd;
+        }
+        // every shared-memory value of plane k is in registers now: hand its stage back to the producer
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&empty[sc]);
+          if (k == len) mbar_arrive(&empty[sn]);  // the plane above the chunk is not read again either
+        }
+        if (MODE == MODE_APPLY) {
+          if (row0) {
+            *reinterpret_cast<double2*>(o0 + ci) = make_double2(qa, qb);
+            acc[0] += pt.x * qa + pt.y * qb;
+          }
+          if (row1) {
+            *reinterpret_cast<double2*>(o0 + ci + D.nx) = make_double2(qc, qd);
+            acc[0] += pb.x * qc + pb.y * qd;
+          }
+        } else {
+          const bool z0 = D.z0 + lz == 0, z1 = D.z0 + lz == D.nzg - 1;
+          Faces Fa, Fb;
+          double2 u, v;
+          if (row0) {
+            if (MODE == MODE_INIT) {
+              Fa.diag = diag_of(C, ca, ax0, false, yt, gy == D.ny - 1, z0, z1);
+              Fb.diag = diag_of(C, cb, false, bx1, yt, gy == D.ny - 1, z0, z1);
+            }
+            cell_epilogue<MODE>(C, ca, ax0, false, Fa, pt.x, qa, u.x, v.x, acc);
+            cell_epilogue<MODE>(C, cb, false, bx1, Fb, pt.y, qb, u.y, v.y, acc);
+            if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci) = u;
+            if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci) = v;
+          }
+          if (row1) {
+            if (MODE == MODE_INIT) {
+              Fa.diag = diag_of(C, cc, ax0, false, false, yb, z0, z1);
+              Fb.diag = diag_of(C, cd, false, bx1, false, yb, z0, z1);
+            }
+            cell_epilogue<MODE>(C, cc, ax0, false, Fa, pb.x, qc, u.x, v.x, acc);
+            cell_epilogue<MODE>(C, cd, false, bx1, Fb, pb.y, qd, u.y, v.y, acc);
+            if (MODE != MODE_RESID) *reinterpret_cast<double2*>(o0 + ci + D.nx) = u;
+            if (MODE == MODE_INIT) *reinterpret_cast<double2*>(o1 + ci + D.nx) = v;
+          }
+        }
+        pt = nt;
+        pb = nb;
+        ci += plane;
+      }
+      seq += nplanes;
+    }
+  }
+  block_sum<3>(acc, red);
+  if (tid == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CG vector kernels.  Rows round-robin over a fixed grid; a_P is recomputed from the code byte.
 //   k_cg_update : alpha = r.z / p.q;  x += alpha p;  r -= alpha q;  partials {r.(r/a_P), r.r}
 //   k_cg_dir    : beta = r.z_new / r.z_old;  p = r/a_P + beta p
