@@ -49,6 +49,8 @@ typedef struct keffb200_params {
 #define KEFFB200_F_NO_TMA 1      /* use the plain global-load stencil kernel (debug / odd nx) */
 #define KEFFB200_F_BATCH_GLOBAL 4 /* 2D batches: force the global-memory FP64 kernel (the on-chip
                                     mixed-precision kernel is used when nx<=128, nx%4==0, ny<=128, ny%8==0) */
+#define KEFFB200_F_BATCH_ADDITIVE 16 /* 2D batches: the on-chip kernel with the two-level additive preconditioner
+                                    instead of the on-chip multigrid one (used anyway unless nx, ny are multiples of 16) */
 #define KEFFB200_F_NO_MG 8       /* grid solver: plain diagonally preconditioned CG instead of the
                                     multigrid-preconditioned one (used anyway when nx is odd, the
                                     grid has fewer than 65 cells, ny < 2, or z-slabs are unequal) */

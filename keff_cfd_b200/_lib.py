@@ -31,6 +31,7 @@ F_NO_TMA = 1
 F_ZERO_INIT = 2
 F_BATCH_GLOBAL = 4
 F_NO_MG = 8
+F_BATCH_ADDITIVE = 16
 COMM_ID_BYTES = 128
 
 # every symbol include/keffb200.h declares (tests check the built library exports each of them)

@@ -9,6 +9,7 @@
 // counts are, and per-image results do not depend on the schedule.
 #include "context.cuh"
 #include "batch2d_onchip.cuh"
+#include "batch2d_mg.cuh"
 
 namespace kb {
 
@@ -205,6 +206,9 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
   const bool onchip = !(P.flags & KEFFB200_F_BATCH_GLOBAL) && nx <= 128 && nx % 4 == 0 && ny <= 128 && ny % 8 == 0;
   const uint8_t* m = d_solid + (size_t)first * n;
   double* T = d_T_out ? d_T_out + (size_t)first * n : nullptr;
+  // on-chip multigrid kernel: sides multiples of 16 (four 2x coarsenings down to the dense level)
+  static const bool no_mgk = getenv("KEFFB200_BATCH_NO_MG") != nullptr;
+  const bool mgk = onchip && !no_mgk && !(P.flags & KEFFB200_F_BATCH_ADDITIVE) && nx % 16 == 0 && ny % 16 == 0 && nx >= 16 && ny >= 16;
   if (onchip) {
     CoefF F;
     for (int ph = 0; ph < 2; ph++) {
@@ -217,8 +221,16 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
     static bool attr_set = false;
     if (!attr_set) {
       KB_CUDA(cudaFuncSetAttribute(k_batch2d_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
+      KB_CUDA(cudaFuncSetAttribute(k_batch2d_mg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM));
       attr_set = true;
     }
+    if (mgk) {
+      static const float om = getenv("KEFFB200_BATCH_OMEGA") ? (float)atof(getenv("KEFFB200_BATCH_OMEGA")) : 0.85f;
+      static const double delta2 = getenv("KEFFB200_BATCH_DELTA") ? atof(getenv("KEFFB200_BATCH_DELTA")) : 1e-4;
+      k_batch2d_mg<<<grid, MB_THREADS, MB_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual, P.flux_balance,
+                                                        (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, om, delta2,
+                                                        ws, T, res + first, counters + slot);
+    } else
     k_batch2d_onchip<<<grid, OC_THREADS, OC_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual,
                                                           P.flux_balance, (long long)P.max_iter,
                                                           (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, T, res + first,
@@ -244,7 +256,9 @@ static int batch2d_workspace(int n_img, int nx, int ny, BatchWs& w) {
   Ctx& c = ctx();
   const size_t n = (size_t)nx * ny;
   const int grid = std::min(n_img, c.sms);
-  const size_t need = (size_t)grid * (4 * n * 8 + n) + (size_t)n_img * sizeof(BatchOut) + 256;
+  // per CTA: 4 FP64 vectors + code bytes (k_batch2d_pcg); k_batch2d_mg needs x + two 64 KB FP32 slices
+  const size_t per_cta = std::max<size_t>(4 * n, mb_ws_stride(n)) * 8;
+  const size_t need = (size_t)grid * (per_cta + n) + (size_t)n_img * sizeof(BatchOut) + 256;
   if (need > c.cap_batch) {
     if (c.batch_ws) cudaFree(c.batch_ws);
     c.batch_ws = nullptr;
@@ -254,7 +268,7 @@ static int batch2d_workspace(int n_img, int nx, int ny, BatchWs& w) {
   }
   char* base = (char*)c.batch_ws;
   w.ws = (double*)base;
-  w.res = (BatchOut*)(base + (size_t)grid * 4 * n * 8);
+  w.res = (BatchOut*)(base + (size_t)grid * per_cta);
   w.counters = (int*)(w.res + n_img);
   w.codes = (uint8_t*)(w.counters + 16);
   return 0;

@@ -1,0 +1,703 @@
+// batch2d_mg.cuh -- 2D batch fast path with an ON-CHIP multigrid preconditioner: one image per SM.
+//
+// Same outer scheme as batch2d_onchip.cuh (FP32 conjugate gradients on chip, FP64 entering through
+// reliable updates: x += y flushed in FP64, true residual b - A x recomputed in FP64 with the FP64
+// coefficients, every stop decision on FP64 quantities), but the preconditioner is one geometric
+// multigrid V(1,1)-cycle instead of D^-1 + a 64-unknown coarse correction: 18 iterations per
+// 128x128 image instead of 153.  The linear system is still exactly the reference's
+// (DiscretizeMatrixCD2D, Keff2D/keff2D.h:482-582); the cycle only changes how fast CG gets there.
+// Replaces the reference batch loop Keff2D/keff2D.cpp:341-471 (SerialGS per image) for images
+// whose sides are multiples of 16 and <= 128; other shapes keep k_batch2d_onchip / k_batch2d_pcg.
+//
+// Hierarchy (all FP32, all in shared memory): level 0 = the image (nx x ny), level l = 2x2
+// aggregates of level l-1, down to level 4 (<= 8x8 = 64 cells) which is solved with a dense inverse
+// (Gauss-Jordan in shared memory once per image).  Transfers are piecewise constant; a coarse face
+// conductance is HALF the sum of the two fine face conductances crossing it (the re-discretised
+// operator on a uniform medium -- same rule as mg.cuh), wall conductances likewise.
+// Cycle, per level with u = D^-1 b:   x1 = w u;   r1 = b - A x1 = (1-w) D u + w sum_f c_f u_nb;
+//   e = coarse(P^T r1);   x2 = x1 + P e;   out = x2 + w D^-1 (b - A x2) = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb
+// -- symmetric positive definite (same D and w on both sides), as CG needs.  x1 and x2 are never stored:
+// a pass reads u (and the coarser correction) of the neighbours and forms them on the fly.
+//
+// Level 0 lives in REGISTERS: a thread owns a 4(x) x 8(y) patch (512 threads, lane -> x, warp -> y), W/E
+// neighbours come from warp shuffles, the rows above/below the patch from a 16 KB exchange buffer in
+// shared memory (each warp publishes its first and last row of u once per cycle).  a_P is the sum of
+// the face conductances that every pass selects from the code bytes anyway, so no 1/a_P array exists.
+// p keeps its guarded shared-memory image (the CG stencil reads neighbours from it); the FP32 vectors
+// y (solution increment) and z (preconditioned residual) are touched only cell-by-cell and stream through
+// a per-CTA slice of global memory that stays L2-resident (128 KB per SM).
+// Per iteration: 3 passes over the image (CG stencil, restrict, post-smoothing), 6 small passes over the
+// coarse levels, one dense 64x64 mat-vec, 12 barriers, one block reduction.
+#pragma once
+#include "batch2d_onchip.cuh"
+
+namespace kb {
+
+constexpr int MB_THREADS = 512, MB_PITCH = 128, MB_ROWS = 130;
+constexpr int MB_NA = 64;  // max cells of the dense level
+__host__ __device__ constexpr int mb_pitch(int L) { return (128 >> L) + 4; }
+__host__ __device__ constexpr int mb_rows(int L) { return (128 >> L) + 2; }
+__host__ __device__ constexpr int mb_n(int L) { return mb_pitch(L) * mb_rows(L); }
+__host__ __device__ constexpr int mb_off(int L) { return L <= 1 ? 0 : mb_off(L - 1) + 5 * mb_n(L - 1); }
+// floats: p image | exchange rows | levels 1..3 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
+//         dense right-hand side | dense inverse | scratch
+constexpr int MB_F_P = 0, MB_F_XCH = MB_F_P + MB_ROWS * MB_PITCH, MB_F_LV = MB_F_XCH + 16 * 2 * 128;
+constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
+constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
+constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 64;
+// per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | x (n)
+__host__ __device__ constexpr size_t mb_ws_stride(size_t n) { return n + 3 * 8192; }
+
+struct Row5 {
+  float cw, c01, c12, c23, ce;  // x faces of a 4-cell row: W of cell 0, 0|1, 1|2, 2|3, E of cell 3
+  float s0, s1, s2, s3;         // S faces
+};
+
+// Face conductances of one row of my patch from its code word (one byte per cell).  left/right: the
+// patch touches the x wall, whose face is a conductance c_wall towards the value 0 (the code bit of a
+// boundary face is clear by construction).  nosouth: the row is the image's last row (adiabatic).
+__device__ __forceinline__ Row5 mb_row(unsigned c, const CoefF& F, bool left, bool right, bool nosouth) {
+  const bool p0 = c & (C_PH << 0), p1 = c & (C_PH << 8), p2 = c & (C_PH << 16), p3 = c & (C_PH << 24);
+  const float a0 = p0 ? F.sx[1] : F.sx[0], a1 = p1 ? F.sx[1] : F.sx[0], a2 = p2 ? F.sx[1] : F.sx[0];
+  const float a3 = p3 ? F.sx[1] : F.sx[0];
+  Row5 r;
+  r.cw = (c & (C_W << 0)) ? F.dx : (left ? (p0 ? F.wall[1] : F.wall[0]) : a0);
+  r.c01 = (c & (C_E << 0)) ? F.dx : a0;
+  r.c12 = (c & (C_E << 8)) ? F.dx : a1;
+  r.c23 = (c & (C_E << 16)) ? F.dx : a2;
+  r.ce = (c & (C_E << 24)) ? F.dx : (right ? (p3 ? F.wall[1] : F.wall[0]) : a3);
+  r.s0 = nosouth ? 0.f : ((c & (C_S << 0)) ? F.dy : (p0 ? F.sy[1] : F.sy[0]));
+  r.s1 = nosouth ? 0.f : ((c & (C_S << 8)) ? F.dy : (p1 ? F.sy[1] : F.sy[0]));
+  r.s2 = nosouth ? 0.f : ((c & (C_S << 16)) ? F.dy : (p2 ? F.sy[1] : F.sy[0]));
+  r.s3 = nosouth ? 0.f : ((c & (C_S << 24)) ? F.dy : (p3 ? F.sy[1] : F.sy[0]));
+  return r;
+}
+// The face conductances are functions of the code words alone; left to itself the compiler computes all of
+// them once per image and keeps ~100 values per thread alive across every pass (= spilled).  Passing the
+// code words through an empty asm at the start of a pass makes it recompute them where they are used.
+__device__ __forceinline__ void mb_fresh(unsigned (&cw)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) asm volatile("" : "+r"(cw[j]));
+}
+// N faces of the patch's first row (the S faces of the row above, seen from this side)
+__device__ __forceinline__ void mb_north(unsigned c, const CoefF& F, bool top, float (&n)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    n[i] = top ? 0.f : ((c & (C_N << (8 * i))) ? F.dy : ((c & (C_PH << (8 * i))) ? F.sy[1] : F.sy[0]));
+}
+
+// ---- coarse levels (shared-memory arrays with a zero guard ring: cell (X,Y) at (Y+1)*pitch + 2 + X) ----
+template <int L>
+struct MbLv {
+  static constexpr int pitch = mb_pitch(L), n = mb_n(L);
+  float *U, *E, *CX, *CY, *DI;
+  __device__ __forceinline__ MbLv(float* lv) {
+    float* b = lv + mb_off(L);
+    U = b;
+    E = b + n;
+    CX = b + 2 * n;
+    CY = b + 3 * n;
+    DI = b + 4 * n;
+  }
+};
+
+// 1/a_P of level L (E holds the wall conductances during setup)
+template <int L>
+__device__ __forceinline__ void mb_dinv(float* lv, int nxl, int nyl, int tid) {
+  MbLv<L> V(lv);
+  constexpr int pt = MbLv<L>::pitch;
+  for (int idx = tid; idx < nxl * nyl; idx += MB_THREADS) {
+    const int Y = idx / nxl, X = idx - Y * nxl, o = (Y + 1) * pt + 2 + X;
+    V.DI[o] = 1.f / (((V.CX[o] + V.CX[o - 1]) + (V.CY[o] + V.CY[o - pt])) + V.E[o]);
+  }
+}
+
+// coefficients of level L+1 from level L (L = 3: into the scratch arrays of the dense level)
+template <int L>
+__device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int nyl, int tid) {
+  MbLv<L> V(lv);
+  constexpr int pt = MbLv<L>::pitch;
+  const int nxc = nxl >> 1, nyc = nyl >> 1;
+  for (int idx = tid; idx < nxc * nyc; idx += MB_THREADS) {
+    const int Yc = idx / nxc, Xc = idx - Yc * nxc, oa = (2 * Yc + 1) * pt + 2 + 2 * Xc;
+    const float cx = 0.5f * (V.CX[oa + 1] + V.CX[oa + pt + 1]);
+    const float cy = 0.5f * (V.CY[oa + pt] + V.CY[oa + pt + 1]);
+    const float wl = 0.5f * ((V.E[oa] + V.E[oa + 1]) + (V.E[oa + pt] + V.E[oa + pt + 1]));
+    if constexpr (L < 3) {
+      MbLv<L + 1> W(lv);
+      const int oc = (Yc + 1) * MbLv<L + 1>::pitch + 2 + Xc;
+      W.CX[oc] = cx;
+      W.CY[oc] = cy;
+      W.E[oc] = wl;
+    } else {
+      scr[idx] = cx;
+      scr[64 + idx] = cy;
+      scr[128 + idx] = wl;
+    }
+  }
+}
+
+// restriction pass of level L: u of level L+1 (or the dense right-hand side) from the residual of x1 = w u
+template <int L>
+__device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, float om, int tid) {
+  MbLv<L> V(lv);
+  constexpr int pt = MbLv<L>::pitch;
+  const int nxc = nxl >> 1, nyc = nyl >> 1;
+  for (int idx = tid; idx < nxc * nyc; idx += MB_THREADS) {
+    const int Yc = idx / nxc, Xc = idx - Yc * nxc;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++) {
+        const int o = (2 * Yc + dy + 1) * pt + 2 + 2 * Xc + dx;
+        const float s = (V.CX[o] * V.U[o + 1] + V.CX[o - 1] * V.U[o - 1]) + (V.CY[o] * V.U[o + pt] + V.CY[o - pt] * V.U[o - pt]);
+        acc += (1.f - om) * __fdividef(V.U[o], V.DI[o]) + om * s;
+      }
+    if constexpr (L < 3) {
+      MbLv<L + 1> W(lv);
+      const int oc = (Yc + 1) * MbLv<L + 1>::pitch + 2 + Xc;
+      W.U[oc] = acc * W.DI[oc];
+    } else {
+      b4[idx] = acc;
+    }
+  }
+}
+
+// post-smoothing pass of level L: E_L = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb,  x2 = w u + P e_{L+1}
+template <int L>
+__device__ __forceinline__ void mb_up(float* lv, const float* e4, int nxl, int nyl, float om, int tid) {
+  MbLv<L> V(lv);
+  constexpr int pt = MbLv<L>::pitch;
+  constexpr int pc = mb_pitch(L + 1);
+  const float* Ec = L < 3 ? lv + mb_off(L < 3 ? L + 1 : 3) + mb_n(L < 3 ? L + 1 : 3) : e4;
+  for (int idx = tid; idx < nxl * nyl; idx += MB_THREADS) {
+    const int Y = idx / nxl, X = idx - Y * nxl, o = (Y + 1) * pt + 2 + X;
+    // aggregate of a cell (arithmetic shifts: -1 -> the guard ring, which holds 0)
+    const int rP = ((Y >> 1) + 1) * pc + 2, rN = (((Y - 1) >> 1) + 1) * pc + 2, rS = (((Y + 1) >> 1) + 1) * pc + 2;
+    const int cP = X >> 1, cW = (X - 1) >> 1, cE = (X + 1) >> 1;
+    const float u = V.U[o];
+    const float xP = om * u + Ec[rP + cP];
+    const float xW = om * V.U[o - 1] + Ec[rP + cW], xE = om * V.U[o + 1] + Ec[rP + cE];
+    const float xN = om * V.U[o - pt] + Ec[rN + cP], xS = om * V.U[o + pt] + Ec[rS + cP];
+    const float s = (V.CX[o] * xE + V.CX[o - 1] * xW) + (V.CY[o] * xS + V.CY[o - pt] * xN);
+    V.E[o] = (1.f - om) * xP + om * u + om * V.DI[o] * s;
+  }
+}
+
+__global__ void __launch_bounds__(MB_THREADS, 1)
+    k_batch2d_mg(const uint8_t* __restrict__ masks, int n_img, int nx, int ny, const Coef C, const CoefF F, double thr2_in,
+                 double flux_tol, long long max_iter, int const_init, float om, double delta2, double* __restrict__ xws,
+                 double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter) {
+  extern __shared__ __align__(16) unsigned char mb_smem[];
+  float* SM = reinterpret_cast<float*>(mb_smem);
+  float* P = SM + MB_F_P;
+  float* XCH = SM + MB_F_XCH;
+  float* LV = SM + MB_F_LV;
+  float* E4 = SM + MB_F_E4;
+  float* B4 = SM + MB_F_B4;
+  float* AI = SM + MB_F_AI;
+  float* scr = SM + MB_F_SCR;
+  double* red = reinterpret_cast<double*>(SM + MB_F_END);
+  double* bc = red + 2 * 64;
+  int* s_img = reinterpret_cast<int*>(bc + 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int x0 = lane * 4, y0 = wrp * 8;
+  const bool act = x0 < nx && y0 < ny;  // shapes are multiples of the patch: all 32 cells in or out
+  const int n = nx * ny;
+  const int nx1 = nx >> 1, ny1 = ny >> 1, nx2 = nx >> 2, ny2 = ny >> 2, nx3 = nx >> 3, ny3 = ny >> 3;
+  const int nax = nx >> 4, na = nax * (ny >> 4);
+  const bool left = x0 == 0, right = x0 + 4 == nx, top = y0 == 0, bot = y0 + 8 == ny;
+  const float om1 = 1.f - om;
+
+  for (int i = tid; i < MB_F_END; i += MB_THREADS) SM[i] = 0.f;  // guard rings stay zero for the whole launch
+  float* Pown = P + (y0 + 1) * MB_PITCH + x0;
+  // y, z, w slices: thread-major float4 rows at compile-time offsets from one base
+  float4* Yg = reinterpret_cast<float4*>(xws + (size_t)blockIdx.x * mb_ws_stride(n)) + tid;
+  constexpr int ZG = 8 * MB_THREADS, WG = 16 * MB_THREADS;  // z and w relative to y (in float4)
+  // level-1 cells of my patch: aggregate rows (y0>>1) + 0..3, aggregate columns (x0>>1) + 0..1
+  MbLv<1> L1(LV);
+  constexpr int p1 = MbLv<1>::pitch;
+  const int o1 = ((y0 >> 1) + 1) * p1 + 2 + (x0 >> 1);
+
+  while (true) {
+    if (tid == 0) *s_img = atomicAdd(counter, 1);
+    __syncthreads();
+    const int img = *s_img;
+    __syncthreads();
+    if (img >= n_img) break;
+    const size_t moff = (size_t)img * n;
+#define MB_M (masks + moff)
+    double* x64 = T_out ? T_out + (size_t)img * n : reinterpret_cast<double*>(Yg - tid) + 3 * 8192;
+
+    // ---- per-image setup: code words (registers), x = initial field, y = 0 ----
+    unsigned cw[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      unsigned cwj = 0;
+      if (act) {
+        const int yy = y0 + j;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int xx = x0 + i, g = yy * nx + xx;
+          const uint8_t* m = MB_M;
+          const unsigned me = m[g] == 1;
+          unsigned c = me;
+          if (xx > 0 && (unsigned)(m[g - 1] == 1) != me) c |= C_W;
+          if (xx < nx - 1 && (unsigned)(m[g + 1] == 1) != me) c |= C_E;
+          if (yy < ny - 1 && (unsigned)(m[g + nx] == 1) != me) c |= C_S;
+          if (yy > 0 && (unsigned)(m[g - nx] == 1) != me) c |= C_N;
+          cwj |= c << (8 * i);
+          x64[g] = const_init ? C.tl : C.tl + (C.tr - C.tl) * ((xx + 0.5) / nx);
+        }
+      }
+      cw[j] = cwj;
+      Yg[j * MB_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- hierarchy: level 1 from the code words, levels 2, 3 and the dense level from the level above ----
+    if (act) {
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const Row5 ra = mb_row(cw[2 * jj], F, left, right, false);
+        const Row5 rb = mb_row(cw[2 * jj + 1], F, left, right, jj == 3 && bot);
+        const unsigned ca = cw[2 * jj], cb = cw[2 * jj + 1];
+        const float wl0 = left ? 0.5f * (((ca & C_PH) ? F.wall[1] : F.wall[0]) + ((cb & C_PH) ? F.wall[1] : F.wall[0])) : 0.f;
+        const float wl1 = right ? 0.5f * (((ca & (C_PH << 24)) ? F.wall[1] : F.wall[0]) + ((cb & (C_PH << 24)) ? F.wall[1] : F.wall[0])) : 0.f;
+        const int o = o1 + jj * p1;
+        *reinterpret_cast<float2*>(L1.CX + o) = make_float2(0.5f * (ra.c12 + rb.c12), right ? 0.f : 0.5f * (ra.ce + rb.ce));
+        *reinterpret_cast<float2*>(L1.CY + o) = make_float2(0.5f * (rb.s0 + rb.s1), 0.5f * (rb.s2 + rb.s3));
+        *reinterpret_cast<float2*>(L1.E + o) = make_float2(wl0, wl1);
+      }
+    }
+    __syncthreads();
+    mb_dinv<1>(LV, nx1, ny1, tid);
+    mb_coarsen<1>(LV, scr, nx1, ny1, tid);
+    __syncthreads();
+    mb_dinv<2>(LV, nx2, ny2, tid);
+    mb_coarsen<2>(LV, scr, nx2, ny2, tid);
+    __syncthreads();
+    mb_dinv<3>(LV, nx3, ny3, tid);
+    mb_coarsen<3>(LV, scr, nx3, ny3, tid);
+    for (int i = tid; i < MB_NA * MB_NA; i += MB_THREADS) AI[i] = 0.f;
+    __syncthreads();
+    if (tid < na) {  // dense level: 5-point matrix on the nax x nay grid
+      const int by = tid / nax, ax = tid - by * nax;
+      const float ce = scr[tid], cs = scr[64 + tid];
+      float dg = ce + cs + scr[128 + tid];
+      if (ax > 0) dg += scr[tid - 1];
+      if (by > 0) dg += scr[64 + tid - nax];
+      AI[tid * MB_NA + tid] = dg;
+      if (ax + 1 < nax) AI[tid * MB_NA + tid + 1] = AI[(tid + 1) * MB_NA + tid] = -ce;
+      if (tid + nax < na) AI[tid * MB_NA + tid + nax] = AI[(tid + nax) * MB_NA + tid] = -cs;
+    }
+    __syncthreads();
+    for (int k = 0; k < na; k++) {  // Gauss-Jordan without pivoting (SPD M-matrix)
+      if (tid < na) {
+        scr[tid] = AI[k * MB_NA + tid];        // pivot row
+        scr[64 + tid] = AI[tid * MB_NA + k];   // pivot column
+      }
+      __syncthreads();
+      const float pinv = 1.f / scr[k];
+      for (int e = tid; e < na * na; e += MB_THREADS) {
+        const int i = e / na, j = e - i * na;
+        float v;
+        if (i == k) v = j == k ? pinv : scr[j] * pinv;
+        else if (j == k) v = -scr[64 + i] * pinv;
+        else v = AI[i * MB_NA + j] - scr[64 + i] * scr[j] * pinv;
+        AI[i * MB_NA + j] = v;
+      }
+      __syncthreads();
+    }
+
+    // ---- the V-cycle: u (= D^-1 a, registers) -> w (registers); swq = sum w.a, szq = sum z.a over my patch ----
+    float u[8][4];
+    auto vcycle = [&](bool with_z, int outg, float& swq, float& szq) {
+      // publish my first and last row of u, then read the rows just above / below the patch
+      if (act) {
+        *reinterpret_cast<float4*>(XCH + (wrp * 2 + 0) * 128 + x0) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
+        *reinterpret_cast<float4*>(XCH + (wrp * 2 + 1) * 128 + x0) = make_float4(u[7][0], u[7][1], u[7][2], u[7][3]);
+      }
+      __syncthreads();
+      // u of the row just above / below my patch (zero outside the image)
+      auto halo = [&](bool north, float (&h)[4]) {
+        h[0] = h[1] = h[2] = h[3] = 0.f;
+        if (act && !(north ? top : bot)) {
+          const float4 t = *reinterpret_cast<const float4*>(XCH + (north ? (wrp - 1) * 2 + 1 : (wrp + 1) * 2) * 128 + x0);
+          h[0] = t.x; h[1] = t.y; h[2] = t.z; h[3] = t.w;
+        }
+      };
+      // ---- level 0, restriction: r1 = (1-w) d u + w sum_f c_f u_nb, summed over 2x2 aggregates ----
+      {
+        mb_fresh(cw);
+        float nn[4];
+        mb_north(cw[0], F, top, nn);
+        float a01 = 0.f, a23 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const Row5 r = mb_row(cw[j], F, left, right, j == 7 && bot);
+          float uw = __shfl_up_sync(0xffffffffu, u[j][3], 1), ue = __shfl_down_sync(0xffffffffu, u[j][0], 1);
+          if (left) uw = 0.f;
+          if (right || lane == 31) ue = 0.f;
+          float un[4], us[4];
+          if (j == 0) halo(true, un);
+          if (j == 7) halo(false, us);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if (j != 0) un[i] = u[j == 0 ? 0 : j - 1][i];
+            if (j != 7) us[i] = u[j == 7 ? 7 : j + 1][i];
+          }
+          const float d0 = (r.cw + r.c01) + (nn[0] + r.s0), d1 = (r.c01 + r.c12) + (nn[1] + r.s1);
+          const float d2 = (r.c12 + r.c23) + (nn[2] + r.s2), d3 = (r.c23 + r.ce) + (nn[3] + r.s3);
+          const float s0 = (r.cw * uw + r.c01 * u[j][1]) + (nn[0] * un[0] + r.s0 * us[0]);
+          const float s1 = (r.c01 * u[j][0] + r.c12 * u[j][2]) + (nn[1] * un[1] + r.s1 * us[1]);
+          const float s2 = (r.c12 * u[j][1] + r.c23 * u[j][3]) + (nn[2] * un[2] + r.s2 * us[2]);
+          const float s3 = (r.c23 * u[j][2] + r.ce * ue) + (nn[3] * un[3] + r.s3 * us[3]);
+          a01 += (om1 * d0 * u[j][0] + om * s0) + (om1 * d1 * u[j][1] + om * s1);
+          a23 += (om1 * d2 * u[j][2] + om * s2) + (om1 * d3 * u[j][3] + om * s3);
+          if (j & 1) {
+            if (act) {
+              const int o = o1 + (j >> 1) * p1;
+              const float2 di = *reinterpret_cast<const float2*>(L1.DI + o);
+              *reinterpret_cast<float2*>(L1.U + o) = make_float2(a01 * di.x, a23 * di.y);
+            }
+            a01 = a23 = 0.f;
+          }
+          nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
+        }
+      }
+      __syncthreads();
+      mb_down<1>(LV, B4, nx1, ny1, om, tid);
+      __syncthreads();
+      mb_down<2>(LV, B4, nx2, ny2, om, tid);
+      __syncthreads();
+      mb_down<3>(LV, B4, nx3, ny3, om, tid);
+      __syncthreads();
+      {  // dense level: e4 = inverse * b4; 8 threads per row
+        const int r = tid >> 3, part = tid & 7;
+        float s = 0.f;
+        if (r < na) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int c = part * 8 + k;
+            if (c < na) s += AI[r * MB_NA + c] * B4[c];
+          }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (part == 0 && r < na) {
+          const int by = r / nax, ax = r - by * nax;
+          E4[(by + 1) * mb_pitch(4) + 2 + ax] = s;
+        }
+      }
+      __syncthreads();
+      mb_up<3>(LV, E4, nx3, ny3, om, tid);
+      __syncthreads();
+      mb_up<2>(LV, E4, nx2, ny2, om, tid);
+      __syncthreads();
+      mb_up<1>(LV, E4, nx1, ny1, om, tid);
+      __syncthreads();
+      // ---- level 0, post-smoothing: w = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb,  x2 = w u + P e1 ----
+      {
+        mb_fresh(cw);
+        float nn[4];
+        mb_north(cw[0], F, top, nn);
+        // corrections of my aggregate rows (own two columns, the column to the left and to the right), of the
+        // aggregate row above the patch and below it
+        float2 eN = make_float2(0.f, 0.f), eS = eN;
+        if (act) {
+          eN = *reinterpret_cast<const float2*>(L1.E + o1 - p1);
+          eS = *reinterpret_cast<const float2*>(L1.E + o1 + 4 * p1);
+        }
+        float xp[4], xc[4], xn[4];  // x2 of the row above, this row, the row below
+        float2 ec = act ? *reinterpret_cast<const float2*>(L1.E + o1) : make_float2(0.f, 0.f);
+        {
+          float hN[4];
+          halo(true, hN);
+          xp[0] = om * hN[0] + eN.x; xp[1] = om * hN[1] + eN.x; xp[2] = om * hN[2] + eN.y; xp[3] = om * hN[3] + eN.y;
+        }
+        xc[0] = om * u[0][0] + ec.x; xc[1] = om * u[0][1] + ec.x; xc[2] = om * u[0][2] + ec.y; xc[3] = om * u[0][3] + ec.y;
+        float sw = 0.f, sz = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const Row5 r = mb_row(cw[j], F, left, right, j == 7 && bot);
+          const int o = o1 + (j >> 1) * p1;
+          float ew = 0.f, ee = 0.f;
+          if (act) {
+            ew = L1.E[o - 1];
+            ee = L1.E[o + 2];
+          }
+          // x2 of the row below: row j+1 of my patch (its aggregate row changes at even j+1) or the halo row
+          float2 en = ec;
+          if (j == 7) en = eS;
+          else if (j & 1) en = act ? *reinterpret_cast<const float2*>(L1.E + o + p1) : make_float2(0.f, 0.f);
+          float ub[4];
+          if (j == 7) halo(false, ub);
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (j != 7) ub[i] = u[j == 7 ? 7 : j + 1][i];
+          xn[0] = om * ub[0] + en.x; xn[1] = om * ub[1] + en.x; xn[2] = om * ub[2] + en.y; xn[3] = om * ub[3] + en.y;
+          float uw = __shfl_up_sync(0xffffffffu, u[j][3], 1), ue = __shfl_down_sync(0xffffffffu, u[j][0], 1);
+          if (left) uw = 0.f;
+          if (right || lane == 31) ue = 0.f;
+          const float xw = om * uw + ew, xe = om * ue + ee;
+          const float d0 = (r.cw + r.c01) + (nn[0] + r.s0), d1 = (r.c01 + r.c12) + (nn[1] + r.s1);
+          const float d2 = (r.c12 + r.c23) + (nn[2] + r.s2), d3 = (r.c23 + r.ce) + (nn[3] + r.s3);
+          const float s0 = (r.cw * xw + r.c01 * xc[1]) + (nn[0] * xp[0] + r.s0 * xn[0]);
+          const float s1 = (r.c01 * xc[0] + r.c12 * xc[2]) + (nn[1] * xp[1] + r.s1 * xn[1]);
+          const float s2 = (r.c12 * xc[1] + r.c23 * xc[3]) + (nn[2] * xp[2] + r.s2 * xn[2]);
+          const float s3 = (r.c23 * xc[2] + r.ce * xe) + (nn[3] * xp[3] + r.s3 * xn[3]);
+          float4 wv;
+          wv.x = om1 * xc[0] + om * u[j][0] + om * __fdividef(s0, d0);
+          wv.y = om1 * xc[1] + om * u[j][1] + om * __fdividef(s1, d1);
+          wv.z = om1 * xc[2] + om * u[j][2] + om * __fdividef(s2, d2);
+          wv.w = om1 * xc[3] + om * u[j][3] + om * __fdividef(s3, d3);
+          if (!act) wv = make_float4(0.f, 0.f, 0.f, 0.f);
+          Yg[outg + j * MB_THREADS] = wv;
+          const float q0 = d0 * u[j][0], q1 = d1 * u[j][1], q2 = d2 * u[j][2], q3 = d3 * u[j][3];  // a = D u
+          sw += (wv.x * q0 + wv.y * q1) + (wv.z * q2 + wv.w * q3);
+          if (with_z) {
+            const float4 zv = Yg[ZG + j * MB_THREADS];
+            sz += (zv.x * q0 + zv.y * q1) + (zv.z * q2 + zv.w * q3);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            xp[i] = xc[i];
+            xc[i] = xn[i];
+          }
+          ec = en;
+          nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
+        }
+        swq = act ? sw : 0.f;
+        szq = act ? sz : 0.f;
+      }
+    };
+
+    double rz = 0, rz_flush = 0, rr_true = 0, bb = 0, r1 = 0, ratio = 1, thr2 = thr2_in;
+    double ql = 0, qr = 0;
+    long long it = 0;
+    int status = 1;
+    bool first = true, restart = false;
+
+    while (true) {
+      // ================= reliable update: x += y (FP64), y = 0, z = M (b - A x), residual in FP64 =================
+      if (!first) {
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 yv = Yg[j * MB_THREADS];
+            double2* xp = reinterpret_cast<double2*>(x64 + (y0 + j) * nx + x0);
+            double2 a = xp[0], b = xp[1];
+            a.x += yv.x; a.y += yv.y; b.x += yv.z; b.y += yv.w;
+            xp[0] = a; xp[1] = b;
+            Yg[j * MB_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        __syncthreads();
+      }
+      double s4[4] = {0, 0, 0, 0};
+      if (act) {
+        mb_fresh(cw);
+        float nn[4];
+        mb_north(cw[0], F, top, nn);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int yy = y0 + j;
+          const bool yt = yy == 0, yb = yy == ny - 1;
+          const unsigned cwj = cw[j];
+          const Row5 r = mb_row(cwj, F, left, right, j == 7 && bot);
+          const float dd[4] = {(r.cw + r.c01) + (nn[0] + r.s0), (r.c01 + r.c12) + (nn[1] + r.s1),
+                               (r.c12 + r.c23) + (nn[2] + r.s2), (r.c23 + r.ce) + (nn[3] + r.s3)};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int xx = x0 + i, g = yy * nx + xx;
+            const bool xl = xx == 0, xr = xx == nx - 1;
+            const unsigned c = (cwj >> (8 * i)) & 0xffu;
+            const Faces Fc = faces_of(C, c, xl, xr, yt, yb, true, true);
+            const double xc = x64[g];
+            double qv = Fc.diag * xc;
+            if (!xl) qv -= Fc.w * x64[g - 1];
+            if (!xr) qv -= Fc.e * x64[g + 1];
+            if (!yt) qv -= Fc.n * x64[g - nx];
+            if (!yb) qv -= Fc.s * x64[g + nx];
+            const double b = rhs_of(C, c, xl, xr), rv = b - qv;
+            u[j][i] = __fdividef((float)rv, dd[i]);
+            s4[1] += rv * rv;
+            s4[2] += b * b;
+            s4[3] += fabs(rv);
+          }
+          nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) u[j][i] = 0.f;
+      }
+      {
+        float swq, szq;
+        vcycle(false, ZG, swq, szq);  // z = M r straight into its slice
+        s4[0] = (double)swq;         // r.z, r rounded to FP32
+      }
+      block_allsum<4>(s4, red, bc);
+      rz = s4[0];
+      rr_true = s4[1];
+      r1 = s4[3];
+      if (first) bb = s4[2];
+      rz_flush = rz;
+      ratio = rz > 0 ? rr_true / rz : 1.0;
+      if (first || restart) {  // p = z (start, or restart after a window that did not reach its target)
+        if (act)
+#pragma unroll
+          for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = Yg[ZG + j * MB_THREADS];
+        first = false;
+        restart = false;
+        __syncthreads();
+      }
+      // ---- stop decisions use only FP64 quantities of the flushed field ----
+      const bool conv = !(rr_true > thr2 * bb);
+      if (conv || it >= max_iter) {
+        double f2[2] = {0, 0};
+        const uint8_t* m = MB_M;
+        for (int row = tid; row < ny; row += MB_THREADS) {
+          const int l = row * nx, e = l + nx - 1;
+          f2[0] += ((m[l] == 1) ? C.wall[1] : C.wall[0]) * (x64[l] - C.tl);
+          f2[1] += ((m[e] == 1) ? C.wall[1] : C.wall[0]) * (C.tr - x64[e]);
+        }
+        block_allsum<2>(f2, red, bc);
+        ql = f2[0];
+        qr = f2[1];
+        const double keff = (ql + qr) / 2 / (C.tr - C.tl);
+        if (conv && (fabs(ql - qr) <= flux_tol * fabs(keff) || thr2 < 1e-28)) {
+          status = 0;
+          break;
+        }
+        if (it >= max_iter) break;
+        thr2 *= 1e-2;
+        if (!(rr_true > thr2 * bb)) continue;  // still satisfied: re-evaluate with the tighter target
+      }
+
+      // ================================ FP32 CG iterations ================================
+      const double rz_stop = fmax(delta2 * rz_flush, thr2 * bb / ratio);
+      bool broke = false;
+      while (true) {
+        float spq = 0.f, szq = 0.f, swq = 0.f;
+        {  // q = A p from the guarded image of p; u = q / a_P
+          mb_fresh(cw);
+          float nn[4];
+          mb_north(cw[0], F, top, nn);
+          float4 hn = *reinterpret_cast<const float4*>(Pown - MB_PITCH);
+          float4 pc = *reinterpret_cast<const float4*>(Pown);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 pn = *reinterpret_cast<const float4*>(Pown + (j + 1) * MB_PITCH);
+            float pw = __shfl_up_sync(0xffffffffu, pc.w, 1), pe = __shfl_down_sync(0xffffffffu, pc.x, 1);
+            if (left) pw = 0.f;
+            if (right || lane == 31) pe = 0.f;
+            const Row5 r = mb_row(cw[j], F, left, right, j == 7 && bot);
+            const float f01 = r.c01 * (pc.x - pc.y), f12 = r.c12 * (pc.y - pc.z), f23 = r.c23 * (pc.z - pc.w);
+            const float q0 = (r.cw * (pc.x - pw) + f01) + (nn[0] * (pc.x - hn.x) + r.s0 * (pc.x - pn.x));
+            const float q1 = (f12 - f01) + (nn[1] * (pc.y - hn.y) + r.s1 * (pc.y - pn.y));
+            const float q2 = (f23 - f12) + (nn[2] * (pc.z - hn.z) + r.s2 * (pc.z - pn.z));
+            const float q3 = (r.ce * (pc.w - pe) - f23) + (nn[3] * (pc.w - hn.w) + r.s3 * (pc.w - pn.w));
+            const float d0 = (r.cw + r.c01) + (nn[0] + r.s0), d1 = (r.c01 + r.c12) + (nn[1] + r.s1);
+            const float d2 = (r.c12 + r.c23) + (nn[2] + r.s2), d3 = (r.c23 + r.ce) + (nn[3] + r.s3);
+            u[j][0] = __fdividef(q0, d0); u[j][1] = __fdividef(q1, d1); u[j][2] = __fdividef(q2, d2);
+            u[j][3] = __fdividef(q3, d3);
+            spq += (pc.x * q0 + pc.y * q1) + (pc.z * q2 + pc.w * q3);
+            nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
+            hn = pc;
+            pc = pn;
+          }
+          if (!act) {
+            spq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+              for (int i = 0; i < 4; i++) u[j][i] = 0.f;
+          }
+        }
+        vcycle(true, WG, swq, szq);  // w = M q (into its slice), sums w.q and z.q
+        // one barrier per reduction: FP32 inside a warp, FP64 across the 16 warps, every warp sums the 16
+        // partials itself (fixed order -> deterministic); `red` is double-buffered by parity
+        double s3[3];
+        {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            spq += __shfl_xor_sync(0xffffffffu, spq, o);
+            szq += __shfl_xor_sync(0xffffffffu, szq, o);
+            swq += __shfl_xor_sync(0xffffffffu, swq, o);
+          }
+          double* rb = red + (it & 1) * 64;
+          if (lane == 0) {
+            rb[wrp * 4 + 0] = (double)spq;
+            rb[wrp * 4 + 1] = (double)szq;
+            rb[wrp * 4 + 2] = (double)swq;
+          }
+          __syncthreads();
+          const int l16 = lane & 15;
+          s3[0] = rb[l16 * 4 + 0];
+          s3[1] = rb[l16 * 4 + 1];
+          s3[2] = rb[l16 * 4 + 2];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            s3[0] += __shfl_xor_sync(0xffffffffu, s3[0], o);
+            s3[1] += __shfl_xor_sync(0xffffffffu, s3[1], o);
+            s3[2] += __shfl_xor_sync(0xffffffffu, s3[2], o);
+          }
+        }
+        if (!(s3[0] > 0.0)) {  // breakdown (cannot happen for an SPD operator short of NaN)
+          status = 2;
+          broke = true;
+          break;
+        }
+        const double alpha = rz / s3[0];
+        double rzn = rz - 2.0 * alpha * s3[1] + alpha * alpha * s3[2];
+        const bool bad = !(rzn > 0.0);  // recurrence lost positivity: force a reliable update
+        if (bad) rzn = rz * 1e-2;
+        const float al = (float)alpha, be = (float)(rzn / rz);
+        rz = rzn;
+        it++;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float4 pv = *reinterpret_cast<const float4*>(Pown + j * MB_PITCH);
+          float4 yv = Yg[j * MB_THREADS];
+          float4 zv = Yg[ZG + j * MB_THREADS];
+          const float4 wv = Yg[WG + j * MB_THREADS];
+          zv.x -= al * wv.x; zv.y -= al * wv.y; zv.z -= al * wv.z; zv.w -= al * wv.w;
+          yv.x += al * pv.x; yv.y += al * pv.y; yv.z += al * pv.z; yv.w += al * pv.w;
+          pv.x = zv.x + be * pv.x; pv.y = zv.y + be * pv.y; pv.z = zv.z + be * pv.z; pv.w = zv.w + be * pv.w;
+          Yg[j * MB_THREADS] = yv;
+          Yg[ZG + j * MB_THREADS] = zv;
+          if (act) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = pv;
+        }
+        __syncthreads();
+        if (rz < rz_stop || it >= max_iter) break;
+        if (bad || (it & 127) == 0) {  // recurrence lost positivity or stalled: reliable update + CG restart
+          restart = true;
+          break;
+        }
+      }
+      if (broke) break;
+    }
+
+    if (tid == 0) {
+      BatchOut o;
+      o.ql = ql;
+      o.qr = qr;
+      o.rr = rr_true;
+      o.bb = bb;
+      o.r1 = r1;
+      o.it = it;
+      o.status = status;
+      o.pad = 0;
+      res[img] = o;
+    }
+    __syncthreads();
+  }
+}
+
+#undef MB_M
+
+}  // namespace kb
