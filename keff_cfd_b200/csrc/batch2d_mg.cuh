@@ -299,13 +299,22 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
       __syncthreads();
       const float pinv = 1.f / scr[k];
-      for (int e = tid; e < na * na; e += MB_THREADS) {
-        const int i = e / na, j = e - i * na;
-        float v;
-        if (i == k) v = j == k ? pinv : scr[j] * pinv;
-        else if (j == k) v = -scr[64 + i] * pinv;
-        else v = AI[i * MB_NA + j] - scr[64 + i] * scr[j] * pinv;
-        AI[i * MB_NA + j] = v;
+      {  // thread -> row tid / 8, columns (tid % 8) * 8 .. + 7
+        const int i = tid >> 3, j0 = (tid & 7) * 8;
+        if (i < na) {
+          const float ci = scr[64 + i] * pinv;
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) {
+            const int j = j0 + jj;
+            if (j < na) {
+              float v;
+              if (i == k) v = j == k ? pinv : scr[j] * pinv;
+              else if (j == k) v = -ci;
+              else v = AI[i * MB_NA + j] - ci * scr[j];
+              AI[i * MB_NA + j] = v;
+            }
+          }
+        }
       }
       __syncthreads();
     }
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
     double ql = 0, qr = 0;
     long long it = 0;
     int status = 1;
-    bool first = true, restart = false;
+    bool first = true, restart = false, fresh_p = true;  // fresh_p: p has not been set for this image yet
 
     while (true) {
       // ================= reliable update: x += y (FP64), y = 0, z = M (b - A x), residual in FP64 =================
@@ -535,27 +544,12 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 4; i++) u[j][i] = 0.f;
       }
-      {
-        float swq, szq;
-        vcycle(false, ZG, swq, szq);  // z = M r straight into its slice
-        s4[0] = (double)swq;         // r.z, r rounded to FP32
-      }
       block_allsum<4>(s4, red, bc);
-      rz = s4[0];
       rr_true = s4[1];
       r1 = s4[3];
       if (first) bb = s4[2];
-      rz_flush = rz;
-      ratio = rz > 0 ? rr_true / rz : 1.0;
-      if (first || restart) {  // p = z (start, or restart after a window that did not reach its target)
-        if (act)
-#pragma unroll
-          for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = Yg[ZG + j * MB_THREADS];
-        first = false;
-        restart = false;
-        __syncthreads();
-      }
-      // ---- stop decisions use only FP64 quantities of the flushed field ----
+      // ---- stop decisions use only FP64 quantities of the flushed field (and come before the cycle: the last
+      //      reliable update of an image needs no z) ----
       const bool conv = !(rr_true > thr2 * bb);
       if (conv || it >= max_iter) {
         double f2[2] = {0, 0};
@@ -575,7 +569,28 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         }
         if (it >= max_iter) break;
         thr2 *= 1e-2;
-        if (!(rr_true > thr2 * bb)) continue;  // still satisfied: re-evaluate with the tighter target
+        if (!(rr_true > thr2 * bb)) {  // still satisfied: re-evaluate with the tighter target
+          first = false;
+          continue;
+        }
+      }
+      {  // z = M r straight into its slice; r.z with r rounded to FP32
+        float swq, szq;
+        vcycle(false, ZG, swq, szq);
+        double s1[1] = {(double)swq};
+        block_allsum<1>(s1, red, bc);
+        rz = s1[0];
+      }
+      rz_flush = rz;
+      ratio = rz > 0 ? rr_true / rz : 1.0;
+      if (first || restart || fresh_p) {  // p = z (start, or restart after a window that did not reach its target)
+        if (act)
+#pragma unroll
+          for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = Yg[ZG + j * MB_THREADS];
+        first = false;
+        restart = false;
+        fresh_p = false;
+        __syncthreads();
       }
 
       // ================================ FP32 CG iterations ================================
