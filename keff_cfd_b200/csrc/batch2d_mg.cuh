@@ -44,7 +44,7 @@ __host__ __device__ constexpr int mb_off(int L) { return L <= 1 ? 0 : mb_off(L -
 constexpr int MB_F_P = 0, MB_F_XCH = MB_F_P + MB_ROWS * MB_PITCH, MB_F_LV = MB_F_XCH + 16 * 2 * 128;
 constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
 constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
-constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 64;
+constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 16 * 8 + 64;
 // per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | x (n)
 __host__ __device__ constexpr size_t mb_ws_stride(size_t n) { return n + 3 * 8192; }
 
@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   float* scr = SM + MB_F_SCR;
   double* red = reinterpret_cast<double*>(SM + MB_F_END);
   double* bc = red + 2 * 64;
-  int* s_img = reinterpret_cast<int*>(bc + 4);
+  double* SC = bc + 4;  // block-uniform FP64 scalars that are only looked at around reliable updates (every thread
+                        // writes the same value, and only plain assignments -- never read-modify-write): parked here so that they do not occupy registers in the passes
+  int* s_img = reinterpret_cast<int*>(SC + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int x0 = lane * 4, y0 = wrp * 8;
@@ -292,31 +294,33 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       if (tid + nax < na) AI[tid * MB_NA + tid + nax] = AI[(tid + nax) * MB_NA + tid] = -cs;
     }
     __syncthreads();
-    for (int k = 0; k < na; k++) {  // Gauss-Jordan without pivoting (SPD M-matrix)
-      if (tid < na) {
-        scr[tid] = AI[k * MB_NA + tid];        // pivot row
-        scr[64 + tid] = AI[tid * MB_NA + k];   // pivot column
-      }
-      __syncthreads();
-      const float pinv = 1.f / scr[k];
-      {  // thread -> row tid / 8, columns (tid % 8) * 8 .. + 7
-        const int i = tid >> 3, j0 = (tid & 7) * 8;
-        if (i < na) {
-          const float ci = scr[64 + i] * pinv;
-#pragma unroll
-          for (int jj = 0; jj < 8; jj++) {
-            const int j = j0 + jj;
-            if (j < na) {
-              float v;
-              if (i == k) v = j == k ? pinv : scr[j] * pinv;
-              else if (j == k) v = -ci;
-              else v = AI[i * MB_NA + j] - ci * scr[j];
-              AI[i * MB_NA + j] = v;
-            }
-          }
+    // Gauss-Jordan without pivoting (SPD M-matrix), branch-free: with r = pivot row / pivot (r_k = 1 / pivot) and
+    // c = pivot column, every entry becomes (i == k ? r_j : (j == k ? 0 : A_ij) - c_i r_j).  Thread -> row tid / 8,
+    // columns (tid % 8) * 8 .. + 7 (two float4); rows / columns >= na hold zeros and stay zero.
+    {
+      const int gi = tid >> 3, gj = (tid & 7) * 8;
+      float4* arow = reinterpret_cast<float4*>(AI + gi * MB_NA + gj);
+      for (int k = 0; k < na; k++) {
+        if (tid < MB_NA) {
+          const float pinv = 1.f / AI[k * MB_NA + k];
+          scr[tid] = tid == k ? pinv : AI[k * MB_NA + tid] * pinv;  // r
+          scr[64 + tid] = AI[tid * MB_NA + k];                      // c
         }
+        __syncthreads();
+        const float ci = scr[64 + gi];
+        const float4 r0 = *reinterpret_cast<const float4*>(scr + gj), r1 = *reinterpret_cast<const float4*>(scr + gj + 4);
+        float4 a0 = arow[0], a1 = arow[1];
+        const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+          const float keep = gj + jj == k ? 0.f : av[jj];
+          av[jj] = gi == k ? rr[jj] : keep - ci * rr[jj];
+        }
+        arow[0] = make_float4(av[0], av[1], av[2], av[3]);
+        arow[1] = make_float4(av[4], av[5], av[6], av[7]);
+        __syncthreads();
       }
-      __syncthreads();
     }
 
     // ---- the V-cycle: u (= D^-1 a, registers) -> w (registers); swq = sum w.a, szq = sum z.a over my patch ----
@@ -483,8 +487,16 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
     };
 
-    double rz = 0, rz_flush = 0, rr_true = 0, bb = 0, r1 = 0, ratio = 1, thr2 = thr2_in;
-    double ql = 0, qr = 0;
+    double rz = 0, thr2 = thr2_in;  // thr2 is updated multiplicatively: it stays a per-thread register
+#define S_rz_flush SC[0]
+#define S_rr_true SC[1]
+#define S_bb SC[2]
+#define S_r1 SC[3]
+#define S_ratio SC[4]
+#define S_ql SC[6]
+#define S_qr SC[7]
+#define S_rz_stop SC[8]
+    S_rz_flush = 0; S_rr_true = 0; S_bb = 0; S_r1 = 0; S_ratio = 1;  S_ql = 0; S_qr = 0;
     long long it = 0;
     int status = 1;
     bool first = true, restart = false, fresh_p = true;  // fresh_p: p has not been set for this image yet
@@ -545,12 +557,12 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           for (int i = 0; i < 4; i++) u[j][i] = 0.f;
       }
       block_allsum<4>(s4, red, bc);
-      rr_true = s4[1];
-      r1 = s4[3];
-      if (first) bb = s4[2];
+      S_rr_true = s4[1];
+      S_r1 = s4[3];
+      if (first) S_bb = s4[2];
       // ---- stop decisions use only FP64 quantities of the flushed field (and come before the cycle: the last
       //      reliable update of an image needs no z) ----
-      const bool conv = !(rr_true > thr2 * bb);
+      const bool conv = !(S_rr_true > thr2 * S_bb);
       if (conv || it >= max_iter) {
         double f2[2] = {0, 0};
         const uint8_t* m = MB_M;
@@ -560,16 +572,16 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           f2[1] += ((m[e] == 1) ? C.wall[1] : C.wall[0]) * (C.tr - x64[e]);
         }
         block_allsum<2>(f2, red, bc);
-        ql = f2[0];
-        qr = f2[1];
-        const double keff = (ql + qr) / 2 / (C.tr - C.tl);
-        if (conv && (fabs(ql - qr) <= flux_tol * fabs(keff) || thr2 < 1e-28)) {
+        S_ql = f2[0];
+        S_qr = f2[1];
+        const double keff = (S_ql + S_qr) / 2 / (C.tr - C.tl);
+        if (conv && (fabs(S_ql - S_qr) <= flux_tol * fabs(keff) || thr2 < 1e-28)) {
           status = 0;
           break;
         }
         if (it >= max_iter) break;
         thr2 *= 1e-2;
-        if (!(rr_true > thr2 * bb)) {  // still satisfied: re-evaluate with the tighter target
+        if (!(S_rr_true > thr2 * S_bb)) {  // still satisfied: re-evaluate with the tighter target
           first = false;
           continue;
         }
@@ -581,8 +593,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         block_allsum<1>(s1, red, bc);
         rz = s1[0];
       }
-      rz_flush = rz;
-      ratio = rz > 0 ? rr_true / rz : 1.0;
+      S_rz_flush = rz;
+      S_ratio = rz > 0 ? S_rr_true / rz : 1.0;
       if (first || restart || fresh_p) {  // p = z (start, or restart after a window that did not reach its target)
         if (act)
 #pragma unroll
@@ -594,7 +606,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
 
       // ================================ FP32 CG iterations ================================
-      const double rz_stop = fmax(delta2 * rz_flush, thr2 * bb / ratio);
+      S_rz_stop = fmax(delta2 * S_rz_flush, thr2 * S_bb / S_ratio);
       bool broke = false;
       while (true) {
         float spq = 0.f, szq = 0.f, swq = 0.f;
@@ -688,7 +700,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           if (act) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = pv;
         }
         __syncthreads();
-        if (rz < rz_stop || it >= max_iter) break;
+        if (rz < S_rz_stop || it >= max_iter) break;
         if (bad || (it & 127) == 0) {  // recurrence lost positivity or stalled: reliable update + CG restart
           restart = true;
           break;
@@ -699,11 +711,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
 
     if (tid == 0) {
       BatchOut o;
-      o.ql = ql;
-      o.qr = qr;
-      o.rr = rr_true;
-      o.bb = bb;
-      o.r1 = r1;
+      o.ql = S_ql;
+      o.qr = S_qr;
+      o.rr = S_rr_true;
+      o.bb = S_bb;
+      o.r1 = S_r1;
       o.it = it;
       o.status = status;
       o.pad = 0;
@@ -714,5 +726,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
 }
 
 #undef MB_M
+#undef S_rz_flush
+#undef S_rr_true
+#undef S_bb
+#undef S_r1
+#undef S_ratio
+#undef S_ql
+#undef S_qr
+#undef S_rz_stop
 
 }  // namespace kb

@@ -241,3 +241,40 @@ def test_onchip_mixed_precision_batch_equals_fp64_batch(K):
     b = K.solve2d_batch(imgs[:8], K.default_params(flags=K.F_BATCH_GLOBAL, **p))
     for f, s in zip(a, b):
         assert f["status"] == 0 and rel(f["keff"], s["keff"]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (64, 96), (16, 16), (112, 48)])
+def test_batch_multigrid_kernel_against_additive_and_fp64_kernels(K, shape):
+    """The three batch kernels -- on-chip multigrid (default for sides that are multiples of 16), on-chip two-level
+    additive (F_BATCH_ADDITIVE), all-FP64 global-memory CG (F_BATCH_GLOBAL) -- solve the same systems; the multigrid
+    one needs an order of magnitude fewer iterations."""
+    from keff_cfd_b200 import structures as S
+    ny, nx = shape
+    imgs = np.stack([S.disc_image(i, n=128)[:ny, :nx] for i in range(12)])
+    mg = K.solve2d_batch(imgs, want_T=True)
+    add = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_ADDITIVE), want_T=True)
+    ref = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_GLOBAL), want_T=True)
+    for m, a, r in zip(mg, add, ref):
+        assert m["status"] == 0 and m["rel_residual"] <= 1e-8                 # TRUE FP64 residual of the returned field
+        assert abs(m["q_left"] - m["q_right"]) <= 1e-6 * m["keff"]
+        assert rel(m["keff"], r["keff"]) < 1e-6 and rel(m["keff"], a["keff"]) < 1e-6
+        assert np.abs(m["T"] - r["T"]).max() < 5e-6
+    if min(shape) >= 64:
+        assert np.mean([m["iters"] for m in mg]) * 4 < np.mean([a["iters"] for a in add])
+
+
+def test_batch_multigrid_kernel_contrast_and_flags(K):
+    """Conductivity ratios from 1:1 to 1e4:1, reversed gradient, the reference's constant start."""
+    from keff_cfd_b200 import structures as S
+    imgs = S.disc_images(6)
+    for ks, kf in ((1.0, 1.0), (100.0, 1.0), (1.0, 50.0), (1e4, 1.0)):
+        p = dict(ks=ks, kf=kf, tl=2.0, tr=-1.0)
+        a = K.solve2d_batch(imgs, K.default_params(**p))
+        b = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_GLOBAL, **p))
+        for f, s in zip(a, b):
+            assert f["status"] == 0 and f["rel_residual"] <= 1e-8 and rel(f["keff"], s["keff"]) < 1e-5
+        if ks == kf:
+            assert all(rel(f["keff"], ks) < 1e-9 for f in a)              # homogeneous medium: Keff = k exactly
+    z = K.solve2d_batch(imgs, K.default_params(flags=K.F_ZERO_INIT))
+    w = K.solve2d_batch(imgs)
+    assert all(x["status"] == 0 and rel(x["keff"], y["keff"]) < 1e-6 for x, y in zip(z, w))
