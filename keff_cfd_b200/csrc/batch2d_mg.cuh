@@ -505,14 +505,26 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       // ================= reliable update: x += y (FP64), y = 0, z = M (b - A x), residual in FP64 =================
       if (!first) {
         if (act) {
+          // all loads of four rows before their stores (x and y may alias as far as the compiler knows, which would
+          // chain eight L2 round trips)
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float4 yv = Yg[j * MB_THREADS];
-            double2* xp = reinterpret_cast<double2*>(x64 + (y0 + j) * nx + x0);
-            double2 a = xp[0], b = xp[1];
-            a.x += yv.x; a.y += yv.y; b.x += yv.z; b.y += yv.w;
-            xp[0] = a; xp[1] = b;
-            Yg[j * MB_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int h = 0; h < 8; h += 4) {
+            float4 yv[4];
+            double2 xa[4], xb[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              yv[j] = Yg[(h + j) * MB_THREADS];
+              const double2* xp = reinterpret_cast<const double2*>(x64 + (y0 + h + j) * nx + x0);
+              xa[j] = xp[0];
+              xb[j] = xp[1];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              double2* xp = reinterpret_cast<double2*>(x64 + (y0 + h + j) * nx + x0);
+              xp[0] = make_double2(xa[j].x + yv[j].x, xa[j].y + yv[j].y);
+              xp[1] = make_double2(xb[j].x + yv[j].z, xb[j].y + yv[j].w);
+              Yg[(h + j) * MB_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
         __syncthreads();
