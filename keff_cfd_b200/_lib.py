@@ -102,6 +102,19 @@ def init(device=0):
         _inited = device
 
 
+def ensure(device=None, tensor=None):
+    """One process is bound to ONE GPU.  device=None keeps the binding made by init() (binding to GPU 0 if there
+    is none yet); an explicit device re-binds only if it differs.  A CUDA tensor argument must live on the bound
+    GPU -- a kernel launched on another device would fault on its address (or, with peer access enabled, silently
+    run every rank's work on one GPU)."""
+    if device is None:
+        device = _inited if _inited is not None else (tensor.device.index if tensor is not None and tensor.is_cuda else 0)
+    init(device)
+    if tensor is not None and getattr(tensor, "is_cuda", False) and tensor.device.index != _inited:
+        raise KeffB200Error(f"tensor lives on cuda:{tensor.device.index} but this process is bound to cuda:{_inited}")
+    return _inited
+
+
 def shutdown():
     global _inited
     if _lib is not None:

@@ -121,10 +121,10 @@ def _res(r, **extra):
     return d
 
 
-def solve3d(solid, params=None, T_init=None, want_T=True, want_q=False, device=0):
+def solve3d(solid, params=None, T_init=None, want_T=True, want_q=False, device=None):
     """One volume.  ``solid``: u8 [nz, ny, nx] numpy array / pinned torch tensor (host path: the copy
     to the GPU is part of the call) or CUDA torch tensor (device path)."""
-    _lib.init(device)
+    device = _lib.ensure(device, solid if _is_cuda(solid) else None)
     p = params or default_params()
     nz, ny, nx = solid.shape
     r = Result()
@@ -144,7 +144,7 @@ def solve3d(solid, params=None, T_init=None, want_T=True, want_q=False, device=0
     return _res(r, T=T, qL=qL, qR=qR)
 
 
-def solve2d(solid, params=None, T_init=None, want_T=True, want_q=False, device=0):
+def solve2d(solid, params=None, T_init=None, want_T=True, want_q=False, device=None):
     """One image: u8 [ny, nx], 1 = solid."""
     out = solve3d(solid.reshape((1,) + tuple(solid.shape)), params, None if T_init is None else T_init.reshape(
         (1,) + tuple(T_init.shape)), want_T, want_q, device)
@@ -154,11 +154,11 @@ def solve2d(solid, params=None, T_init=None, want_T=True, want_q=False, device=0
     return out
 
 
-def solve2d_batch(solid, params=None, want_T=False, device=0):
+def solve2d_batch(solid, params=None, want_T=False, device=None):
     """A batch of images u8 [n_img, ny, nx]; returns the per-image result records as a numpy
     structured array (res[i]["keff"], res["iters"], ...), or a list of dicts that also carry the
     temperature maps under "T" when want_T."""
-    _lib.init(device)
+    device = _lib.ensure(device, solid if _is_cuda(solid) else None)
     p = params or default_params()
     n, ny, nx = solid.shape
     res = (Result * n)()
@@ -180,9 +180,9 @@ def solve2d_batch(solid, params=None, want_T=False, device=0):
     return out
 
 
-def apply_operator(solid, x, params=None, want_b=False, device=0):
+def apply_operator(solid, x, params=None, want_b=False, device=None):
     """y = A x (and b) for the matrix-free form of the reference's assembled system."""
-    _lib.init(device)
+    device = _lib.ensure(device)
     p = params or default_params()
     solid = np.ascontiguousarray(solid, dtype=np.uint8)
     if solid.ndim == 2:
@@ -195,9 +195,9 @@ def apply_operator(solid, x, params=None, want_b=False, device=0):
     return (y, b) if want_b else y
 
 
-def precondition(solid, r, params=None, device=0):
+def precondition(solid, r, params=None, device=None):
     """z = M r: one multigrid V-cycle of the grid solver's preconditioner (test hook)."""
-    _lib.init(device)
+    device = _lib.ensure(device)
     p = params or default_params()
     solid = np.ascontiguousarray(solid, dtype=np.uint8)
     if solid.ndim == 2:
@@ -209,9 +209,9 @@ def precondition(solid, r, params=None, device=0):
     return z
 
 
-def boundary_flux(solid, T, params=None, device=0):
+def boundary_flux(solid, T, params=None, device=None):
     """Flux integration + energy residual of a given field (Keff2D/keff2D.cpp:151-170, keff2D.h:384)."""
-    _lib.init(device)
+    device = _lib.ensure(device)
     p = params or default_params()
     solid = np.ascontiguousarray(solid, dtype=np.uint8)
     if solid.ndim == 2:
@@ -224,9 +224,9 @@ def boundary_flux(solid, T, params=None, device=0):
     return _res(r, qL=qL, qR=qR)
 
 
-def bench_apply(solid_dev, params=None, reps=20, device=0):
+def bench_apply(solid_dev, params=None, reps=20, device=None):
     """Average ms per stencil application on a device-resident structure (CUDA events)."""
-    _lib.init(device)
+    device = _lib.ensure(device, solid_dev)
     p = params or default_params()
     nz, ny, nx = solid_dev.shape
     ms = C.c_float()
@@ -234,10 +234,10 @@ def bench_apply(solid_dev, params=None, reps=20, device=0):
     return ms.value
 
 
-def bernoulli_volume_dev(shape, p=0.5, seed=1234, z0=0, device=0):
+def bernoulli_volume_dev(shape, p=0.5, seed=1234, z0=0, device=None):
     """Device-side twin of structures.bernoulli_volume: CUDA u8 tensor [nz, ny, nx]."""
     import torch
-    _lib.init(device)
+    device = _lib.ensure(device)
     nz, ny, nx = shape
     out = torch.empty(shape, dtype=torch.uint8, device=f"cuda:{device}")
     check(lib().keffb200_gen_bernoulli_dev(out.data_ptr(), nz * ny * nx, z0 * ny * nx, seed, p))

@@ -902,6 +902,21 @@ static int stage_mask(const uint8_t* src, bool src_is_device, const Dom& D) {
   return 0;
 }
 
+// a device-buffer entry point was handed memory of another GPU: refuse (a kernel on this device would fault on
+// it, or -- with peer access enabled -- silently do another rank's work here)
+static int check_dev_ptr(const void* p, const char* what) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(KEFFB200_EINVAL, "%s: not a CUDA pointer", what);
+  }
+  if (a.type == cudaMemoryTypeDevice && a.device != ctx().device)
+    return fail(KEFFB200_EINVAL, "%s lives on device %d but the library is bound to device %d", what, a.device, ctx().device);
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+    return fail(KEFFB200_EINVAL, "%s: expected device memory", what);
+  return 0;
+}
+
 static int need_ready() {
   if (!ctx().ready) return fail(KEFFB200_ESTATE, "keffb200_init has not been called");
   return 0;
@@ -1058,6 +1073,7 @@ int keffb200_solve3d_dev(const uint8_t* d_solid, int nx, int ny, int nz, const k
                          const double* d_T_init, double* d_T_out, keffb200_result* out) {
   KB_TRY(need_ready());
   if (!d_solid || !out) return fail(KEFFB200_EINVAL, "null argument");
+  KB_TRY(check_dev_ptr(d_solid, "d_solid"));
   const keffb200_params P = norm_params(p);
   Dom D{nx, ny, nz, 0, nz};
   if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
@@ -1069,6 +1085,7 @@ int keffb200_solve3d_slab_dev(const uint8_t* d_solid_halo, int nx, int ny, int n
                               const keffb200_params* p, double* d_T_out, keffb200_result* out) {
   KB_TRY(need_ready());
   if (!d_solid_halo || !out) return fail(KEFFB200_EINVAL, "null argument");
+  KB_TRY(check_dev_ptr(d_solid_halo, "d_solid_halo"));
   if (z0 < 0 || nz_local < 1 || z0 + nz_local > nz_global) return fail(KEFFB200_EINVAL, "bad slab extent");
   if (ctx().nccl.world > 1 && !ctx().nccl.comm) return fail(KEFFB200_ESTATE, "keffb200_dist_init has not been called");
   const keffb200_params P = norm_params(p);
@@ -1084,6 +1101,7 @@ int keffb200_solve2d_batch_dev(const uint8_t* d_solid, int n_img, int nx, int ny
                                double* d_T_out, keffb200_result* out) {
   KB_TRY(need_ready());
   if (!d_solid || !out || n_img < 1) return fail(KEFFB200_EINVAL, "bad argument");
+  KB_TRY(check_dev_ptr(d_solid, "d_solid"));
   return batch2d_solve_dev(d_solid, n_img, nx, ny, norm_params(p), d_T_out, out);
 }
 
