@@ -86,6 +86,32 @@ __device__ __forceinline__ void mb_north(unsigned c, const CoefF& F, bool top, f
     n[i] = top ? 0.f : ((c & (C_N << (8 * i))) ? F.dy : ((c & (C_PH << (8 * i))) ? F.sy[1] : F.sy[0]));
 }
 
+// the same in FP64 with the FP64 coefficients (true residual of the reliable updates)
+struct Row5d {
+  double cw, c01, c12, c23, ce, s0, s1, s2, s3;
+};
+__device__ __forceinline__ Row5d mb_row_d(unsigned c, const Coef& C, bool left, bool right, bool nosouth) {
+  const bool p0 = c & (C_PH << 0), p1 = c & (C_PH << 8), p2 = c & (C_PH << 16), p3 = c & (C_PH << 24);
+  const double sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0], sy1 = C.same[1][1];
+  const double a0 = p0 ? sx1 : sx0, a1 = p1 ? sx1 : sx0, a2 = p2 ? sx1 : sx0, a3 = p3 ? sx1 : sx0;
+  Row5d r;
+  r.cw = (c & (C_W << 0)) ? C.diff[0] : (left ? (p0 ? C.wall[1] : C.wall[0]) : a0);
+  r.c01 = (c & (C_E << 0)) ? C.diff[0] : a0;
+  r.c12 = (c & (C_E << 8)) ? C.diff[0] : a1;
+  r.c23 = (c & (C_E << 16)) ? C.diff[0] : a2;
+  r.ce = (c & (C_E << 24)) ? C.diff[0] : (right ? (p3 ? C.wall[1] : C.wall[0]) : a3);
+  r.s0 = nosouth ? 0.0 : ((c & (C_S << 0)) ? C.diff[1] : (p0 ? sy1 : sy0));
+  r.s1 = nosouth ? 0.0 : ((c & (C_S << 8)) ? C.diff[1] : (p1 ? sy1 : sy0));
+  r.s2 = nosouth ? 0.0 : ((c & (C_S << 16)) ? C.diff[1] : (p2 ? sy1 : sy0));
+  r.s3 = nosouth ? 0.0 : ((c & (C_S << 24)) ? C.diff[1] : (p3 ? sy1 : sy0));
+  return r;
+}
+__device__ __forceinline__ void mb_north_d(unsigned c, const Coef& C, bool top, double (&n)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    n[i] = top ? 0.0 : ((c & (C_N << (8 * i))) ? C.diff[1] : ((c & (C_PH << (8 * i))) ? C.same[1][1] : C.same[1][0]));
+}
+
 // ---- coarse levels (shared-memory arrays with a zero guard ring: cell (X,Y) at (Y+1)*pitch + 2 + X) ----
 template <int L>
 struct MbLv {
@@ -531,36 +557,49 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
       double s4[4] = {0, 0, 0, 0};
       if (act) {
+        // TRUE residual in FP64, flux form r_P = sum_f c_f (x_nb - x_P) with the wall a face towards TL / TR; rows of x
+        // roll through registers (each value is loaded once), the FP64 face conductances are selected per row
         mb_fresh(cw);
         float nn[4];
+        double nd[4];
         mb_north(cw[0], F, top, nn);
+        mb_north_d(cw[0], C, top, nd);
+        auto load_row = [&](int yy, double (&v)[4]) {
+          const double2* xp = reinterpret_cast<const double2*>(x64 + yy * nx + x0);
+          const double2 a = xp[0], b = xp[1];
+          v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        };
+        double xn[4] = {0, 0, 0, 0}, xc[4], xs[4];
+        if (!top) load_row(y0 - 1, xn);
+        load_row(y0, xc);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const int yy = y0 + j;
-          const bool yt = yy == 0, yb = yy == ny - 1;
+          if (j == 7 && bot) xs[0] = xs[1] = xs[2] = xs[3] = 0.0;
+          else load_row(yy + 1, xs);
+          const double xw = left ? C.tl : x64[yy * nx + x0 - 1], xe = right ? C.tr : x64[yy * nx + x0 + 4];
           const unsigned cwj = cw[j];
           const Row5 r = mb_row(cwj, F, left, right, j == 7 && bot);
+          const Row5d rd = mb_row_d(cwj, C, left, right, j == 7 && bot);
           const float dd[4] = {(r.cw + r.c01) + (nn[0] + r.s0), (r.c01 + r.c12) + (nn[1] + r.s1),
                                (r.c12 + r.c23) + (nn[2] + r.s2), (r.c23 + r.ce) + (nn[3] + r.s3)};
+          const double f01 = rd.c01 * (xc[1] - xc[0]), f12 = rd.c12 * (xc[2] - xc[1]), f23 = rd.c23 * (xc[3] - xc[2]);
+          const double rv[4] = {(rd.cw * (xw - xc[0]) + f01) + (nd[0] * (xn[0] - xc[0]) + rd.s0 * (xs[0] - xc[0])),
+                                (f12 - f01) + (nd[1] * (xn[1] - xc[1]) + rd.s1 * (xs[1] - xc[1])),
+                                (f23 - f12) + (nd[2] * (xn[2] - xc[2]) + rd.s2 * (xs[2] - xc[2])),
+                                (rd.ce * (xe - xc[3]) - f23) + (nd[3] * (xn[3] - xc[3]) + rd.s3 * (xs[3] - xc[3]))};
+          const double b0 = left ? rd.cw * C.tl : 0.0, b3 = right ? rd.ce * C.tr : 0.0;  // right-hand side entries
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const int xx = x0 + i, g = yy * nx + xx;
-            const bool xl = xx == 0, xr = xx == nx - 1;
-            const unsigned c = (cwj >> (8 * i)) & 0xffu;
-            const Faces Fc = faces_of(C, c, xl, xr, yt, yb, true, true);
-            const double xc = x64[g];
-            double qv = Fc.diag * xc;
-            if (!xl) qv -= Fc.w * x64[g - 1];
-            if (!xr) qv -= Fc.e * x64[g + 1];
-            if (!yt) qv -= Fc.n * x64[g - nx];
-            if (!yb) qv -= Fc.s * x64[g + nx];
-            const double b = rhs_of(C, c, xl, xr), rv = b - qv;
-            u[j][i] = __fdividef((float)rv, dd[i]);
-            s4[1] += rv * rv;
-            s4[2] += b * b;
-            s4[3] += fabs(rv);
+            u[j][i] = __fdividef((float)rv[i], dd[i]);
+            s4[1] += rv[i] * rv[i];
+            s4[3] += fabs(rv[i]);
+            xn[i] = xc[i];
+            xc[i] = xs[i];
           }
+          s4[2] += b0 * b0 + b3 * b3;
           nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
+          nd[0] = rd.s0; nd[1] = rd.s1; nd[2] = rd.s2; nd[3] = rd.s3;
         }
       } else {
 #pragma unroll
