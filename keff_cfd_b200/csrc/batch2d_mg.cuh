@@ -39,10 +39,10 @@ __host__ __device__ constexpr int mb_pitch(int L) { return (128 >> L) + 4; }
 __host__ __device__ constexpr int mb_rows(int L) { return (128 >> L) + 2; }
 __host__ __device__ constexpr int mb_n(int L) { return mb_pitch(L) * mb_rows(L); }
 __host__ __device__ constexpr int mb_off(int L) { return L <= 1 ? 0 : mb_off(L - 1) + 5 * mb_n(L - 1); }
-// floats: p image | exchange rows | levels 1..3 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
+// floats: p image | exchange rows | levels 1..4 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
 //         dense right-hand side | dense inverse | scratch
 constexpr int MB_F_P = 0, MB_F_XCH = MB_F_P + MB_ROWS * MB_PITCH, MB_F_LV = MB_F_XCH + 16 * 2 * 128;
-constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
+constexpr int MB_F_E4 = MB_F_LV + mb_off(5), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
 constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
 constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 16 * 8 + 64;
 // per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | x (n)
@@ -138,8 +138,8 @@ __device__ __forceinline__ void mb_dinv(float* lv, int nxl, int nyl, int tid) {
   }
 }
 
-// coefficients of level L+1 from level L (L = 3: into the scratch arrays of the dense level)
-template <int L>
+// coefficients of level L+1 from level L (L = LAST: into the scratch arrays of the dense level)
+template <int L, int LAST>
 __device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int nyl, int tid) {
   MbLv<L> V(lv);
   constexpr int pt = MbLv<L>::pitch;
@@ -149,7 +149,7 @@ __device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int n
     const float cx = 0.5f * (V.CX[oa + 1] + V.CX[oa + pt + 1]);
     const float cy = 0.5f * (V.CY[oa + pt] + V.CY[oa + pt + 1]);
     const float wl = 0.5f * ((V.E[oa] + V.E[oa + 1]) + (V.E[oa + pt] + V.E[oa + pt + 1]));
-    if constexpr (L < 3) {
+    if constexpr (L < LAST) {
       MbLv<L + 1> W(lv);
       const int oc = (Yc + 1) * MbLv<L + 1>::pitch + 2 + Xc;
       W.CX[oc] = cx;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int n
 }
 
 // restriction pass of level L: u of level L+1 (or the dense right-hand side) from the residual of x1 = w u
-template <int L>
+template <int L, int LAST>
 __device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, float om, int tid) {
   MbLv<L> V(lv);
   constexpr int pt = MbLv<L>::pitch;
@@ -180,7 +180,7 @@ __device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, 
         const float s = (V.CX[o] * V.U[o + 1] + V.CX[o - 1] * V.U[o - 1]) + (V.CY[o] * V.U[o + pt] + V.CY[o - pt] * V.U[o - pt]);
         acc += (1.f - om) * __fdividef(V.U[o], V.DI[o]) + om * s;
       }
-    if constexpr (L < 3) {
+    if constexpr (L < LAST) {
       MbLv<L + 1> W(lv);
       const int oc = (Yc + 1) * MbLv<L + 1>::pitch + 2 + Xc;
       W.U[oc] = acc * W.DI[oc];
@@ -191,12 +191,12 @@ __device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, 
 }
 
 // post-smoothing pass of level L: E_L = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb,  x2 = w u + P e_{L+1}
-template <int L>
+template <int L, int LAST>
 __device__ __forceinline__ void mb_up(float* lv, const float* e4, int nxl, int nyl, float om, int tid) {
   MbLv<L> V(lv);
   constexpr int pt = MbLv<L>::pitch;
   constexpr int pc = mb_pitch(L + 1);
-  const float* Ec = L < 3 ? lv + mb_off(L < 3 ? L + 1 : 3) + mb_n(L < 3 ? L + 1 : 3) : e4;
+  const float* Ec = L < LAST ? lv + mb_off(L < LAST ? L + 1 : LAST) + mb_n(L < LAST ? L + 1 : LAST) : e4;
   for (int idx = tid; idx < nxl * nyl; idx += MB_THREADS) {
     const int Y = idx / nxl, X = idx - Y * nxl, o = (Y + 1) * pt + 2 + X;
     // aggregate of a cell (arithmetic shifts: -1 -> the guard ring, which holds 0)
@@ -211,9 +211,82 @@ __device__ __forceinline__ void mb_up(float* lv, const float* e4, int nxl, int n
   }
 }
 
+// ---- level 1 with the thread layout of level 0: a thread owns the 2(x) x 4(y) level-1 cells under its patch ----
+// (the generic passes above spend most of their instructions on index arithmetic and scalar loads; level 1 holds
+// 3/4 of all coarse cells).  o = array offset of my first cell; rows -1 and 4 / columns -1 and 2 are my neighbours'
+// cells or the zero guard ring.
+struct MbBlk1 {
+  float2 U[6];        // rows -1 .. 4
+  float uw[4], ue[4]; // columns -1 and 2 of rows 0 .. 3
+  float2 cx[4], di[4], cy[5];  // cy rows -1 .. 3
+  float cxw[4];
+};
+__device__ __forceinline__ void mb_load1(float* lv, int o, MbBlk1& B) {
+  MbLv<1> V(lv);
+  constexpr int pt = MbLv<1>::pitch;
+#pragma unroll
+  for (int r = 0; r < 6; r++) B.U[r] = *reinterpret_cast<const float2*>(V.U + o + (r - 1) * pt);
+#pragma unroll
+  for (int r = 0; r < 5; r++) B.cy[r] = *reinterpret_cast<const float2*>(V.CY + o + (r - 1) * pt);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    B.uw[r] = V.U[o + r * pt - 1];
+    B.ue[r] = V.U[o + r * pt + 2];
+    B.cx[r] = *reinterpret_cast<const float2*>(V.CX + o + r * pt);
+    B.cxw[r] = V.CX[o + r * pt - 1];
+    B.di[r] = *reinterpret_cast<const float2*>(V.DI + o + r * pt);
+  }
+}
+// restriction: the two level-2 cells (column lane, rows 2 wrp + {0, 1}) under my block
+__device__ __forceinline__ void mb_down1(float* lv, int o, int lane, int wrp, float om) {
+  MbBlk1 B;
+  mb_load1(lv, o, B);
+  MbLv<2> W(lv);
+  float acc[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const float2 u = B.U[r + 1], un = B.U[r], us = B.U[r + 2];
+    const float sa = (B.cx[r].x * u.y + B.cxw[r] * B.uw[r]) + (B.cy[r + 1].x * us.x + B.cy[r].x * un.x);
+    const float sb = (B.cx[r].y * B.ue[r] + B.cx[r].x * u.x) + (B.cy[r + 1].y * us.y + B.cy[r].y * un.y);
+    acc[r >> 1] += (1.f - om) * (__fdividef(u.x, B.di[r].x) + __fdividef(u.y, B.di[r].y)) + om * (sa + sb);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int oc = (2 * wrp + k + 1) * MbLv<2>::pitch + 2 + lane;
+    W.U[oc] = acc[k] * W.DI[oc];
+  }
+}
+// post-smoothing: E1 of my block from U1 and the level-2 correction
+__device__ __forceinline__ void mb_up1(float* lv, int o, int lane, int wrp, float om) {
+  MbBlk1 B;
+  mb_load1(lv, o, B);
+  MbLv<1> V(lv);
+  MbLv<2> W(lv);
+  constexpr int pt = MbLv<1>::pitch, p2 = MbLv<2>::pitch;
+  const int c2 = (2 * wrp + 1) * p2 + 2 + lane;  // level-2 cell under my rows 0, 1
+  const float e0 = W.E[c2], e1 = W.E[c2 + p2], en = W.E[c2 - p2], es = W.E[c2 + 2 * p2];
+  const float ew0 = W.E[c2 - 1], ew1 = W.E[c2 + p2 - 1], ee0 = W.E[c2 + 1], ee1 = W.E[c2 + p2 + 1];
+  float2 x[6];  // x2 = w u + P e of rows -1 .. 4
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const float e = r == 0 ? en : (r <= 2 ? e0 : (r <= 4 ? e1 : es));
+    x[r] = make_float2(om * B.U[r].x + e, om * B.U[r].y + e);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const float xw = om * B.uw[r] + (r < 2 ? ew0 : ew1), xe = om * B.ue[r] + (r < 2 ? ee0 : ee1);
+    const float2 xc = x[r + 1], xn = x[r], xs = x[r + 2], u = B.U[r + 1];
+    const float sa = (B.cx[r].x * xc.y + B.cxw[r] * xw) + (B.cy[r + 1].x * xs.x + B.cy[r].x * xn.x);
+    const float sb = (B.cx[r].y * xe + B.cx[r].x * xc.x) + (B.cy[r + 1].y * xs.y + B.cy[r].y * xn.y);
+    *reinterpret_cast<float2*>(V.E + o + r * pt) =
+        make_float2((1.f - om) * xc.x + om * u.x + om * B.di[r].x * sa, (1.f - om) * xc.y + om * u.y + om * B.di[r].y * sb);
+  }
+}
+
 __global__ void __launch_bounds__(MB_THREADS, 1)
     k_batch2d_mg(const uint8_t* __restrict__ masks, int n_img, int nx, int ny, const Coef C, const CoefF F, double thr2_in,
-                 double flux_tol, long long max_iter, int const_init, float om, double delta2, double* __restrict__ xws,
+                 double flux_tol, long long max_iter, int const_init, float om, double delta2, int allow_deep,
+                 double* __restrict__ xws,
                  double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter) {
   extern __shared__ __align__(16) unsigned char mb_smem[];
   float* SM = reinterpret_cast<float*>(mb_smem);
@@ -235,7 +308,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   const bool act = x0 < nx && y0 < ny;  // shapes are multiples of the patch: all 32 cells in or out
   const int n = nx * ny;
   const int nx1 = nx >> 1, ny1 = ny >> 1, nx2 = nx >> 2, ny2 = ny >> 2, nx3 = nx >> 3, ny3 = ny >> 3;
-  const int nax = nx >> 4, na = nax * (ny >> 4);
+  // sides that are multiples of 32 take one more level: the dense level is then 4 x 4 (<= 16 unknowns) instead of
+  // 8 x 8, which makes its inversion (once per image) and its mat-vec (every cycle) ~4x cheaper
+  const bool deep = allow_deep && nx % 32 == 0 && ny % 32 == 0;
+  const int nx4 = nx >> 4, ny4 = ny >> 4;
+  const int nax = deep ? nx >> 5 : nx4, na = nax * (deep ? ny >> 5 : ny4);
   const bool left = x0 == 0, right = x0 + 4 == nx, top = y0 == 0, bot = y0 + 8 == ny;
   const float om1 = 1.f - om;
 
@@ -300,13 +377,20 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
     }
     __syncthreads();
     mb_dinv<1>(LV, nx1, ny1, tid);
-    mb_coarsen<1>(LV, scr, nx1, ny1, tid);
+    mb_coarsen<1, 4>(LV, scr, nx1, ny1, tid);
     __syncthreads();
     mb_dinv<2>(LV, nx2, ny2, tid);
-    mb_coarsen<2>(LV, scr, nx2, ny2, tid);
+    mb_coarsen<2, 4>(LV, scr, nx2, ny2, tid);
     __syncthreads();
     mb_dinv<3>(LV, nx3, ny3, tid);
-    mb_coarsen<3>(LV, scr, nx3, ny3, tid);
+    if (deep) {
+      mb_coarsen<3, 4>(LV, scr, nx3, ny3, tid);
+      __syncthreads();
+      mb_dinv<4>(LV, nx4, ny4, tid);
+      mb_coarsen<4, 4>(LV, scr, nx4, ny4, tid);
+    } else {
+      mb_coarsen<3, 3>(LV, scr, nx3, ny3, tid);
+    }
     for (int i = tid; i < MB_NA * MB_NA; i += MB_THREADS) AI[i] = 0.f;
     __syncthreads();
     if (tid < na) {  // dense level: 5-point matrix on the nax x nay grid
@@ -406,11 +490,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         }
       }
       __syncthreads();
-      mb_down<1>(LV, B4, nx1, ny1, om, tid);
+      if (act) mb_down1(LV, o1, lane, wrp, om);
       __syncthreads();
-      mb_down<2>(LV, B4, nx2, ny2, om, tid);
+      mb_down<2, 4>(LV, B4, nx2, ny2, om, tid);
       __syncthreads();
-      mb_down<3>(LV, B4, nx3, ny3, om, tid);
+      if (deep) {
+        mb_down<3, 4>(LV, B4, nx3, ny3, om, tid);
+        __syncthreads();
+        mb_down<4, 4>(LV, B4, nx4, ny4, om, tid);
+      } else {
+        mb_down<3, 3>(LV, B4, nx3, ny3, om, tid);
+      }
       __syncthreads();
       {  // dense level: e4 = inverse * b4; 8 threads per row
         const int r = tid >> 3, part = tid & 7;
@@ -427,15 +517,21 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (part == 0 && r < na) {
           const int by = r / nax, ax = r - by * nax;
-          E4[(by + 1) * mb_pitch(4) + 2 + ax] = s;
+          E4[(by + 1) * (deep ? mb_pitch(5) : mb_pitch(4)) + 2 + ax] = s;
         }
       }
       __syncthreads();
-      mb_up<3>(LV, E4, nx3, ny3, om, tid);
+      if (deep) {
+        mb_up<4, 4>(LV, E4, nx4, ny4, om, tid);
+        __syncthreads();
+        mb_up<3, 4>(LV, E4, nx3, ny3, om, tid);
+      } else {
+        mb_up<3, 3>(LV, E4, nx3, ny3, om, tid);
+      }
       __syncthreads();
-      mb_up<2>(LV, E4, nx2, ny2, om, tid);
+      mb_up<2, 4>(LV, E4, nx2, ny2, om, tid);
       __syncthreads();
-      mb_up<1>(LV, E4, nx1, ny1, om, tid);
+      if (act) mb_up1(LV, o1, lane, wrp, om);
       __syncthreads();
       // ---- level 0, post-smoothing: w = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb,  x2 = w u + P e1 ----
       {
