@@ -225,11 +225,17 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
       attr_set = true;
     }
     if (mgk) {
-      static const float om = getenv("KEFFB200_BATCH_OMEGA") ? (float)atof(getenv("KEFFB200_BATCH_OMEGA")) : 0.85f;
-      static const int deep = getenv("KEFFB200_BATCH_DEEP") ? atoi(getenv("KEFFB200_BATCH_DEEP")) : 0;
-      static const double delta2 = getenv("KEFFB200_BATCH_DELTA") ? atof(getenv("KEFFB200_BATCH_DELTA")) : 1e-4;
+      static const float om = getenv("KEFFB200_BATCH_OMEGA") ? (float)atof(getenv("KEFFB200_BATCH_OMEGA")) : 0.8f;
+      // smoothing weights of the coarse levels (two sweeps per side); "w1,w2" overrides
+      static float wc1 = 0.7f, wc2 = 1.4f;
+      static bool wc_read = false;
+      if (!wc_read) {
+        if (const char* e = getenv("KEFFB200_BATCH_WC")) sscanf(e, "%f,%f", &wc1, &wc2);
+        wc_read = true;
+      }
+      static const double delta2 = getenv("KEFFB200_BATCH_DELTA") ? atof(getenv("KEFFB200_BATCH_DELTA")) : 1e-5;
       k_batch2d_mg<<<grid, MB_THREADS, MB_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual, P.flux_balance,
-                                                        (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, om, delta2, deep,
+                                                        (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, om, wc1, wc2, delta2,
                                                         ws, T, res + first, counters + slot);
     } else
     k_batch2d_onchip<<<grid, OC_THREADS, OC_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual,

@@ -39,10 +39,14 @@ __host__ __device__ constexpr int mb_pitch(int L) { return (128 >> L) + 4; }
 __host__ __device__ constexpr int mb_rows(int L) { return (128 >> L) + 2; }
 __host__ __device__ constexpr int mb_n(int L) { return mb_pitch(L) * mb_rows(L); }
 __host__ __device__ constexpr int mb_off(int L) { return L <= 1 ? 0 : mb_off(L - 1) + 5 * mb_n(L - 1); }
-// floats: p image | exchange rows | levels 1..4 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
+// floats: p image | exchange rows = X1 | X2 | X3 | levels 1..3 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
 //         dense right-hand side | dense inverse | scratch
-constexpr int MB_F_P = 0, MB_F_XCH = MB_F_P + MB_ROWS * MB_PITCH, MB_F_LV = MB_F_XCH + 16 * 2 * 128;
-constexpr int MB_F_E4 = MB_F_LV + mb_off(5), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
+// The iterates X of levels 1..3 start at the exchange rows: X1 overlays them (they are dead once every thread holds
+// its halo rows in registers, and X1 is dead again when the next cycle publishes new rows).
+constexpr int MB_F_P = 0, MB_F_XCH = MB_F_P + MB_ROWS * MB_PITCH, MB_F_X2 = MB_F_XCH + mb_n(1), MB_F_X3 = MB_F_X2 + mb_n(2);
+constexpr int MB_F_LV = MB_F_X3 + mb_n(3);
+static_assert(mb_n(1) >= 16 * 2 * 128, "X1 must cover the exchange rows");
+constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
 constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
 constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 16 * 8 + 64;
 // per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | x (n)
@@ -138,8 +142,8 @@ __device__ __forceinline__ void mb_dinv(float* lv, int nxl, int nyl, int tid) {
   }
 }
 
-// coefficients of level L+1 from level L (L = LAST: into the scratch arrays of the dense level)
-template <int L, int LAST>
+// coefficients of level L+1 from level L (L = 3: into the scratch arrays of the dense level)
+template <int L>
 __device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int nyl, int tid) {
   MbLv<L> V(lv);
   constexpr int pt = MbLv<L>::pitch;
@@ -149,7 +153,7 @@ __device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int n
     const float cx = 0.5f * (V.CX[oa + 1] + V.CX[oa + pt + 1]);
     const float cy = 0.5f * (V.CY[oa + pt] + V.CY[oa + pt + 1]);
     const float wl = 0.5f * ((V.E[oa] + V.E[oa + 1]) + (V.E[oa + pt] + V.E[oa + pt + 1]));
-    if constexpr (L < LAST) {
+    if constexpr (L < 3) {
       MbLv<L + 1> W(lv);
       const int oc = (Yc + 1) * MbLv<L + 1>::pitch + 2 + Xc;
       W.CX[oc] = cx;
@@ -163,9 +167,39 @@ __device__ __forceinline__ void mb_coarsen(float* lv, float* scr, int nxl, int n
   }
 }
 
-// restriction pass of level L: u of level L+1 (or the dense right-hand side) from the residual of x1 = w u
-template <int L, int LAST>
-__device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, float om, int tid) {
+// Coarse levels run nu = 2 sweeps on either side of their coarse correction (weights w1, w2 before, w2, w1 after),
+// which needs one stored iterate X per level:
+//   A: X = x2 = (w1 + w2 - w1 w2) u + w1 w2 D^-1 sum c u_nb            (x1 = w1 u is implicit)
+//   B: restrict  D (u - x2) + sum c x2_nb  -> u of the next level
+//   C: E = x4 = (1 - w2) x3 + w2 u + w2 D^-1 sum c x3_nb,  x3 = x2 + P e_next
+//   D: X = x5 = (1 - w1) x4 + w1 u + w1 D^-1 sum c x4_nb                (the level's correction e = x5)
+// A, C, D are one routine: out_P = a x_P + b u_P + g D^-1_P sum_f c_f x_nb with x = in (+ Ec of the aggregate).
+// Guard cells of `in` / Ec only ever meet a zero conductance, so they need to be finite, not zero.
+template <int L, bool ADD>
+__device__ __forceinline__ void mb_sweep(float* lv, const float* in, const float* Ec, float* out, int nxl, int nyl, float a,
+                                         float b, float g, int tid) {
+  MbLv<L> V(lv);
+  constexpr int pt = MbLv<L>::pitch;
+  constexpr int pc = mb_pitch(L + 1);
+  for (int idx = tid; idx < nxl * nyl; idx += MB_THREADS) {
+    const int Y = idx / nxl, X = idx - Y * nxl, o = (Y + 1) * pt + 2 + X;
+    float xP = in[o], xW = in[o - 1], xE = in[o + 1], xN = in[o - pt], xS = in[o + pt];
+    if (ADD) {  // aggregate of a cell (arithmetic shifts: -1 -> the guard ring)
+      const int rP = ((Y >> 1) + 1) * pc + 2, rN = (((Y - 1) >> 1) + 1) * pc + 2, rS = (((Y + 1) >> 1) + 1) * pc + 2;
+      const int cP = X >> 1, cW = (X - 1) >> 1, cE = (X + 1) >> 1;
+      xP += Ec[rP + cP];
+      xW += Ec[rP + cW];
+      xE += Ec[rP + cE];
+      xN += Ec[rN + cP];
+      xS += Ec[rS + cP];
+    }
+    const float sm = (V.CX[o] * xE + V.CX[o - 1] * xW) + (V.CY[o] * xS + V.CY[o - pt] * xN);
+    out[o] = a * xP + b * V.U[o] + g * V.DI[o] * sm;
+  }
+}
+
+template <int L>
+__device__ __forceinline__ void mb_restrict(float* lv, const float* in, float* b4, int nxl, int nyl, int tid) {
   MbLv<L> V(lv);
   constexpr int pt = MbLv<L>::pitch;
   const int nxc = nxl >> 1, nyc = nyl >> 1;
@@ -177,10 +211,10 @@ __device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, 
 #pragma unroll
       for (int dx = 0; dx < 2; dx++) {
         const int o = (2 * Yc + dy + 1) * pt + 2 + 2 * Xc + dx;
-        const float s = (V.CX[o] * V.U[o + 1] + V.CX[o - 1] * V.U[o - 1]) + (V.CY[o] * V.U[o + pt] + V.CY[o - pt] * V.U[o - pt]);
-        acc += (1.f - om) * __fdividef(V.U[o], V.DI[o]) + om * s;
+        const float sm = (V.CX[o] * in[o + 1] + V.CX[o - 1] * in[o - 1]) + (V.CY[o] * in[o + pt] + V.CY[o - pt] * in[o - pt]);
+        acc += __fdividef(V.U[o] - in[o], V.DI[o]) + sm;
       }
-    if constexpr (L < LAST) {
+    if constexpr (L < 3) {
       MbLv<L + 1> W(lv);
       const int oc = (Yc + 1) * MbLv<L + 1>::pitch + 2 + Xc;
       W.U[oc] = acc * W.DI[oc];
@@ -190,65 +224,76 @@ __device__ __forceinline__ void mb_down(float* lv, float* b4, int nxl, int nyl, 
   }
 }
 
-// post-smoothing pass of level L: E_L = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb,  x2 = w u + P e_{L+1}
-template <int L, int LAST>
-__device__ __forceinline__ void mb_up(float* lv, const float* e4, int nxl, int nyl, float om, int tid) {
-  MbLv<L> V(lv);
-  constexpr int pt = MbLv<L>::pitch;
-  constexpr int pc = mb_pitch(L + 1);
-  const float* Ec = L < LAST ? lv + mb_off(L < LAST ? L + 1 : LAST) + mb_n(L < LAST ? L + 1 : LAST) : e4;
-  for (int idx = tid; idx < nxl * nyl; idx += MB_THREADS) {
-    const int Y = idx / nxl, X = idx - Y * nxl, o = (Y + 1) * pt + 2 + X;
-    // aggregate of a cell (arithmetic shifts: -1 -> the guard ring, which holds 0)
-    const int rP = ((Y >> 1) + 1) * pc + 2, rN = (((Y - 1) >> 1) + 1) * pc + 2, rS = (((Y + 1) >> 1) + 1) * pc + 2;
-    const int cP = X >> 1, cW = (X - 1) >> 1, cE = (X + 1) >> 1;
-    const float u = V.U[o];
-    const float xP = om * u + Ec[rP + cP];
-    const float xW = om * V.U[o - 1] + Ec[rP + cW], xE = om * V.U[o + 1] + Ec[rP + cE];
-    const float xN = om * V.U[o - pt] + Ec[rN + cP], xS = om * V.U[o + pt] + Ec[rS + cP];
-    const float s = (V.CX[o] * xE + V.CX[o - 1] * xW) + (V.CY[o] * xS + V.CY[o - pt] * xN);
-    V.E[o] = (1.f - om) * xP + om * u + om * V.DI[o] * s;
-  }
-}
-
 // ---- level 1 with the thread layout of level 0: a thread owns the 2(x) x 4(y) level-1 cells under its patch ----
-// (the generic passes above spend most of their instructions on index arithmetic and scalar loads; level 1 holds
-// 3/4 of all coarse cells).  o = array offset of my first cell; rows -1 and 4 / columns -1 and 2 are my neighbours'
-// cells or the zero guard ring.
+// (the generic passes spend most of their instructions on index arithmetic and scalar loads; level 1 holds 3/4 of
+// all coarse cells).  o = array offset of my first cell; rows -1 and 4 / columns -1 and 2 are my neighbours' cells
+// or the guard ring.
 struct MbBlk1 {
-  float2 U[6];        // rows -1 .. 4
-  float uw[4], ue[4]; // columns -1 and 2 of rows 0 .. 3
+  float2 I[6];         // input field, rows -1 .. 4
+  float iw[4], ie[4];  // its columns -1 and 2, rows 0 .. 3
+  float2 u[4];         // u of my cells
   float2 cx[4], di[4], cy[5];  // cy rows -1 .. 3
   float cxw[4];
 };
-__device__ __forceinline__ void mb_load1(float* lv, int o, MbBlk1& B) {
+template <bool IN_IS_U>
+__device__ __forceinline__ void mb_load1(float* lv, const float* in, int o, MbBlk1& B) {
   MbLv<1> V(lv);
   constexpr int pt = MbLv<1>::pitch;
 #pragma unroll
-  for (int r = 0; r < 6; r++) B.U[r] = *reinterpret_cast<const float2*>(V.U + o + (r - 1) * pt);
+  for (int r = 0; r < 6; r++) B.I[r] = *reinterpret_cast<const float2*>(in + o + (r - 1) * pt);
 #pragma unroll
   for (int r = 0; r < 5; r++) B.cy[r] = *reinterpret_cast<const float2*>(V.CY + o + (r - 1) * pt);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    B.uw[r] = V.U[o + r * pt - 1];
-    B.ue[r] = V.U[o + r * pt + 2];
+    B.iw[r] = in[o + r * pt - 1];
+    B.ie[r] = in[o + r * pt + 2];
+    B.u[r] = IN_IS_U ? B.I[r + 1] : *reinterpret_cast<const float2*>(V.U + o + r * pt);
     B.cx[r] = *reinterpret_cast<const float2*>(V.CX + o + r * pt);
     B.cxw[r] = V.CX[o + r * pt - 1];
     B.di[r] = *reinterpret_cast<const float2*>(V.DI + o + r * pt);
   }
 }
-// restriction: the two level-2 cells (column lane, rows 2 wrp + {0, 1}) under my block
-__device__ __forceinline__ void mb_down1(float* lv, int o, int lane, int wrp, float om) {
+// passes A, C, D on my block; Ec = correction of level 2 (ADD)
+template <bool ADD, bool IN_IS_U>
+__device__ __forceinline__ void mb_sweep1(float* lv, const float* in, const float* Ec, float* out, int o, int lane, int wrp,
+                                          float a, float b, float g) {
   MbBlk1 B;
-  mb_load1(lv, o, B);
+  mb_load1<IN_IS_U>(lv, in, o, B);
+  constexpr int pt = MbLv<1>::pitch, p2 = MbLv<2>::pitch;
+  float ew0 = 0.f, ew1 = 0.f, ee0 = 0.f, ee1 = 0.f;
+  if (ADD) {
+    const int c2 = (2 * wrp + 1) * p2 + 2 + lane;  // level-2 cell under my rows 0, 1
+    const float e0 = Ec[c2], e1 = Ec[c2 + p2], en = Ec[c2 - p2], es = Ec[c2 + 2 * p2];
+    ew0 = Ec[c2 - 1]; ew1 = Ec[c2 + p2 - 1]; ee0 = Ec[c2 + 1]; ee1 = Ec[c2 + p2 + 1];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const float e = r == 0 ? en : (r <= 2 ? e0 : (r <= 4 ? e1 : es));
+      B.I[r].x += e;
+      B.I[r].y += e;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const float xw = B.iw[r] + (r < 2 ? ew0 : ew1), xe = B.ie[r] + (r < 2 ? ee0 : ee1);
+    const float2 xc = B.I[r + 1], xn = B.I[r], xs = B.I[r + 2];
+    const float sa = (B.cx[r].x * xc.y + B.cxw[r] * xw) + (B.cy[r + 1].x * xs.x + B.cy[r].x * xn.x);
+    const float sb = (B.cx[r].y * xe + B.cx[r].x * xc.x) + (B.cy[r + 1].y * xs.y + B.cy[r].y * xn.y);
+    *reinterpret_cast<float2*>(out + o + r * pt) =
+        make_float2(a * xc.x + b * B.u[r].x + g * B.di[r].x * sa, a * xc.y + b * B.u[r].y + g * B.di[r].y * sb);
+  }
+}
+// pass B on my block: the two level-2 cells (column lane, rows 2 wrp + {0, 1}) under it
+__device__ __forceinline__ void mb_restrict1(float* lv, const float* in, int o, int lane, int wrp) {
+  MbBlk1 B;
+  mb_load1<false>(lv, in, o, B);
   MbLv<2> W(lv);
   float acc[2] = {0.f, 0.f};
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    const float2 u = B.U[r + 1], un = B.U[r], us = B.U[r + 2];
-    const float sa = (B.cx[r].x * u.y + B.cxw[r] * B.uw[r]) + (B.cy[r + 1].x * us.x + B.cy[r].x * un.x);
-    const float sb = (B.cx[r].y * B.ue[r] + B.cx[r].x * u.x) + (B.cy[r + 1].y * us.y + B.cy[r].y * un.y);
-    acc[r >> 1] += (1.f - om) * (__fdividef(u.x, B.di[r].x) + __fdividef(u.y, B.di[r].y)) + om * (sa + sb);
+    const float2 xc = B.I[r + 1], xn = B.I[r], xs = B.I[r + 2];
+    const float sa = (B.cx[r].x * xc.y + B.cxw[r] * B.iw[r]) + (B.cy[r + 1].x * xs.x + B.cy[r].x * xn.x);
+    const float sb = (B.cx[r].y * B.ie[r] + B.cx[r].x * xc.x) + (B.cy[r + 1].y * xs.y + B.cy[r].y * xn.y);
+    acc[r >> 1] += (__fdividef(B.u[r].x - xc.x, B.di[r].x) + __fdividef(B.u[r].y - xc.y, B.di[r].y)) + (sa + sb);
   }
 #pragma unroll
   for (int k = 0; k < 2; k++) {
@@ -256,42 +301,19 @@ __device__ __forceinline__ void mb_down1(float* lv, int o, int lane, int wrp, fl
     W.U[oc] = acc[k] * W.DI[oc];
   }
 }
-// post-smoothing: E1 of my block from U1 and the level-2 correction
-__device__ __forceinline__ void mb_up1(float* lv, int o, int lane, int wrp, float om) {
-  MbBlk1 B;
-  mb_load1(lv, o, B);
-  MbLv<1> V(lv);
-  MbLv<2> W(lv);
-  constexpr int pt = MbLv<1>::pitch, p2 = MbLv<2>::pitch;
-  const int c2 = (2 * wrp + 1) * p2 + 2 + lane;  // level-2 cell under my rows 0, 1
-  const float e0 = W.E[c2], e1 = W.E[c2 + p2], en = W.E[c2 - p2], es = W.E[c2 + 2 * p2];
-  const float ew0 = W.E[c2 - 1], ew1 = W.E[c2 + p2 - 1], ee0 = W.E[c2 + 1], ee1 = W.E[c2 + p2 + 1];
-  float2 x[6];  // x2 = w u + P e of rows -1 .. 4
-#pragma unroll
-  for (int r = 0; r < 6; r++) {
-    const float e = r == 0 ? en : (r <= 2 ? e0 : (r <= 4 ? e1 : es));
-    x[r] = make_float2(om * B.U[r].x + e, om * B.U[r].y + e);
-  }
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const float xw = om * B.uw[r] + (r < 2 ? ew0 : ew1), xe = om * B.ue[r] + (r < 2 ? ee0 : ee1);
-    const float2 xc = x[r + 1], xn = x[r], xs = x[r + 2], u = B.U[r + 1];
-    const float sa = (B.cx[r].x * xc.y + B.cxw[r] * xw) + (B.cy[r + 1].x * xs.x + B.cy[r].x * xn.x);
-    const float sb = (B.cx[r].y * xe + B.cx[r].x * xc.x) + (B.cy[r + 1].y * xs.y + B.cy[r].y * xn.y);
-    *reinterpret_cast<float2*>(V.E + o + r * pt) =
-        make_float2((1.f - om) * xc.x + om * u.x + om * B.di[r].x * sa, (1.f - om) * xc.y + om * u.y + om * B.di[r].y * sb);
-  }
-}
 
 __global__ void __launch_bounds__(MB_THREADS, 1)
     k_batch2d_mg(const uint8_t* __restrict__ masks, int n_img, int nx, int ny, const Coef C, const CoefF F, double thr2_in,
-                 double flux_tol, long long max_iter, int const_init, float om, double delta2, int allow_deep,
+                 double flux_tol, long long max_iter, int const_init, float om, float wc1, float wc2, double delta2,
                  double* __restrict__ xws,
                  double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter) {
   extern __shared__ __align__(16) unsigned char mb_smem[];
   float* SM = reinterpret_cast<float*>(mb_smem);
   float* P = SM + MB_F_P;
   float* XCH = SM + MB_F_XCH;
+  float* X1 = XCH;  // iterates / final corrections of levels 1..3 (X1 overlays the exchange rows)
+  float* X2 = SM + MB_F_X2;
+  float* X3 = SM + MB_F_X3;
   float* LV = SM + MB_F_LV;
   float* E4 = SM + MB_F_E4;
   float* B4 = SM + MB_F_B4;
@@ -308,11 +330,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   const bool act = x0 < nx && y0 < ny;  // shapes are multiples of the patch: all 32 cells in or out
   const int n = nx * ny;
   const int nx1 = nx >> 1, ny1 = ny >> 1, nx2 = nx >> 2, ny2 = ny >> 2, nx3 = nx >> 3, ny3 = ny >> 3;
-  // sides that are multiples of 32 take one more level: the dense level is then 4 x 4 (<= 16 unknowns) instead of
-  // 8 x 8, which makes its inversion (once per image) and its mat-vec (every cycle) ~4x cheaper
-  const bool deep = allow_deep && nx % 32 == 0 && ny % 32 == 0;
-  const int nx4 = nx >> 4, ny4 = ny >> 4;
-  const int nax = deep ? nx >> 5 : nx4, na = nax * (deep ? ny >> 5 : ny4);
+  const int nax = nx >> 4, na = nax * (ny >> 4);
   const bool left = x0 == 0, right = x0 + 4 == nx, top = y0 == 0, bot = y0 + 8 == ny;
   const float om1 = 1.f - om;
 
@@ -323,6 +341,9 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   constexpr int ZG = 8 * MB_THREADS, WG = 16 * MB_THREADS;  // z and w relative to y (in float4)
   // level-1 cells of my patch: aggregate rows (y0>>1) + 0..3, aggregate columns (x0>>1) + 0..1
   MbLv<1> L1(LV);
+  MbLv<2> L2(LV);
+  MbLv<3> L3(LV);
+  const float cA = wc1 + wc2 - wc1 * wc2, cG = wc1 * wc2;  // first stored iterate of a coarse level from u
   constexpr int p1 = MbLv<1>::pitch;
   const int o1 = ((y0 >> 1) + 1) * p1 + 2 + (x0 >> 1);
 
@@ -377,20 +398,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
     }
     __syncthreads();
     mb_dinv<1>(LV, nx1, ny1, tid);
-    mb_coarsen<1, 4>(LV, scr, nx1, ny1, tid);
+    mb_coarsen<1>(LV, scr, nx1, ny1, tid);
     __syncthreads();
     mb_dinv<2>(LV, nx2, ny2, tid);
-    mb_coarsen<2, 4>(LV, scr, nx2, ny2, tid);
+    mb_coarsen<2>(LV, scr, nx2, ny2, tid);
     __syncthreads();
     mb_dinv<3>(LV, nx3, ny3, tid);
-    if (deep) {
-      mb_coarsen<3, 4>(LV, scr, nx3, ny3, tid);
-      __syncthreads();
-      mb_dinv<4>(LV, nx4, ny4, tid);
-      mb_coarsen<4, 4>(LV, scr, nx4, ny4, tid);
-    } else {
-      mb_coarsen<3, 3>(LV, scr, nx3, ny3, tid);
-    }
+    mb_coarsen<3>(LV, scr, nx3, ny3, tid);
     for (int i = tid; i < MB_NA * MB_NA; i += MB_THREADS) AI[i] = 0.f;
     __syncthreads();
     if (tid < na) {  // dense level: 5-point matrix on the nax x nay grid
@@ -442,14 +456,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         *reinterpret_cast<float4*>(XCH + (wrp * 2 + 1) * 128 + x0) = make_float4(u[7][0], u[7][1], u[7][2], u[7][3]);
       }
       __syncthreads();
-      // u of the row just above / below my patch (zero outside the image)
-      auto halo = [&](bool north, float (&h)[4]) {
-        h[0] = h[1] = h[2] = h[3] = 0.f;
-        if (act && !(north ? top : bot)) {
-          const float4 t = *reinterpret_cast<const float4*>(XCH + (north ? (wrp - 1) * 2 + 1 : (wrp + 1) * 2) * 128 + x0);
-          h[0] = t.x; h[1] = t.y; h[2] = t.z; h[3] = t.w;
-        }
-      };
+      // u of the row just above / below my patch (zero outside the image); kept in registers for the post-smoothing
+      // pass because X1 overwrites the exchange rows in between
+      float hN[4] = {0.f, 0.f, 0.f, 0.f}, hS[4] = {0.f, 0.f, 0.f, 0.f};
+      if (act && !top) {
+        const float4 t = *reinterpret_cast<const float4*>(XCH + ((wrp - 1) * 2 + 1) * 128 + x0);
+        hN[0] = t.x; hN[1] = t.y; hN[2] = t.z; hN[3] = t.w;
+      }
+      if (act && !bot) {
+        const float4 t = *reinterpret_cast<const float4*>(XCH + ((wrp + 1) * 2) * 128 + x0);
+        hS[0] = t.x; hS[1] = t.y; hS[2] = t.z; hS[3] = t.w;
+      }
       // ---- level 0, restriction: r1 = (1-w) d u + w sum_f c_f u_nb, summed over 2x2 aggregates ----
       {
         mb_fresh(cw);
@@ -463,12 +480,10 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           if (left) uw = 0.f;
           if (right || lane == 31) ue = 0.f;
           float un[4], us[4];
-          if (j == 0) halo(true, un);
-          if (j == 7) halo(false, us);
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            if (j != 0) un[i] = u[j == 0 ? 0 : j - 1][i];
-            if (j != 7) us[i] = u[j == 7 ? 7 : j + 1][i];
+            un[i] = j == 0 ? hN[i] : u[j == 0 ? 0 : j - 1][i];
+            us[i] = j == 7 ? hS[i] : u[j == 7 ? 7 : j + 1][i];
           }
           const float d0 = (r.cw + r.c01) + (nn[0] + r.s0), d1 = (r.c01 + r.c12) + (nn[1] + r.s1);
           const float d2 = (r.c12 + r.c23) + (nn[2] + r.s2), d3 = (r.c23 + r.ce) + (nn[3] + r.s3);
@@ -490,17 +505,18 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         }
       }
       __syncthreads();
-      if (act) mb_down1(LV, o1, lane, wrp, om);
+      // ---- levels 1..3 down: two sweeps (the first implicit), restriction ----
+      if (act) mb_sweep1<false, true>(LV, L1.U, nullptr, X1, o1, lane, wrp, cA, 0.f, cG);
       __syncthreads();
-      mb_down<2, 4>(LV, B4, nx2, ny2, om, tid);
+      if (act) mb_restrict1(LV, X1, o1, lane, wrp);
       __syncthreads();
-      if (deep) {
-        mb_down<3, 4>(LV, B4, nx3, ny3, om, tid);
-        __syncthreads();
-        mb_down<4, 4>(LV, B4, nx4, ny4, om, tid);
-      } else {
-        mb_down<3, 3>(LV, B4, nx3, ny3, om, tid);
-      }
+      mb_sweep<2, false>(LV, L2.U, nullptr, X2, nx2, ny2, cA, 0.f, cG, tid);
+      __syncthreads();
+      mb_restrict<2>(LV, X2, B4, nx2, ny2, tid);
+      __syncthreads();
+      mb_sweep<3, false>(LV, L3.U, nullptr, X3, nx3, ny3, cA, 0.f, cG, tid);
+      __syncthreads();
+      mb_restrict<3>(LV, X3, B4, nx3, ny3, tid);
       __syncthreads();
       {  // dense level: e4 = inverse * b4; 8 threads per row
         const int r = tid >> 3, part = tid & 7;
@@ -517,21 +533,22 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (part == 0 && r < na) {
           const int by = r / nax, ax = r - by * nax;
-          E4[(by + 1) * (deep ? mb_pitch(5) : mb_pitch(4)) + 2 + ax] = s;
+          E4[(by + 1) * mb_pitch(4) + 2 + ax] = s;
         }
       }
       __syncthreads();
-      if (deep) {
-        mb_up<4, 4>(LV, E4, nx4, ny4, om, tid);
-        __syncthreads();
-        mb_up<3, 4>(LV, E4, nx3, ny3, om, tid);
-      } else {
-        mb_up<3, 3>(LV, E4, nx3, ny3, om, tid);
-      }
+      // ---- levels 3..1 up: correction added on the fly, two sweeps; a level's correction ends up in its X ----
+      mb_sweep<3, true>(LV, X3, E4, L3.E, nx3, ny3, 1.f - wc2, wc2, wc2, tid);
       __syncthreads();
-      mb_up<2, 4>(LV, E4, nx2, ny2, om, tid);
+      mb_sweep<3, false>(LV, L3.E, nullptr, X3, nx3, ny3, 1.f - wc1, wc1, wc1, tid);
       __syncthreads();
-      if (act) mb_up1(LV, o1, lane, wrp, om);
+      mb_sweep<2, true>(LV, X2, X3, L2.E, nx2, ny2, 1.f - wc2, wc2, wc2, tid);
+      __syncthreads();
+      mb_sweep<2, false>(LV, L2.E, nullptr, X2, nx2, ny2, 1.f - wc1, wc1, wc1, tid);
+      __syncthreads();
+      if (act) mb_sweep1<true, false>(LV, X1, X2, L1.E, o1, lane, wrp, 1.f - wc2, wc2, wc2);
+      __syncthreads();
+      if (act) mb_sweep1<false, false>(LV, L1.E, nullptr, X1, o1, lane, wrp, 1.f - wc1, wc1, wc1);
       __syncthreads();
       // ---- level 0, post-smoothing: w = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb,  x2 = w u + P e1 ----
       {
@@ -542,16 +559,12 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         // aggregate row above the patch and below it
         float2 eN = make_float2(0.f, 0.f), eS = eN;
         if (act) {
-          eN = *reinterpret_cast<const float2*>(L1.E + o1 - p1);
-          eS = *reinterpret_cast<const float2*>(L1.E + o1 + 4 * p1);
+          eN = *reinterpret_cast<const float2*>(X1 + o1 - p1);
+          eS = *reinterpret_cast<const float2*>(X1 + o1 + 4 * p1);
         }
         float xp[4], xc[4], xn[4];  // x2 of the row above, this row, the row below
-        float2 ec = act ? *reinterpret_cast<const float2*>(L1.E + o1) : make_float2(0.f, 0.f);
-        {
-          float hN[4];
-          halo(true, hN);
-          xp[0] = om * hN[0] + eN.x; xp[1] = om * hN[1] + eN.x; xp[2] = om * hN[2] + eN.y; xp[3] = om * hN[3] + eN.y;
-        }
+        float2 ec = act ? *reinterpret_cast<const float2*>(X1 + o1) : make_float2(0.f, 0.f);
+        xp[0] = om * hN[0] + eN.x; xp[1] = om * hN[1] + eN.x; xp[2] = om * hN[2] + eN.y; xp[3] = om * hN[3] + eN.y;
         xc[0] = om * u[0][0] + ec.x; xc[1] = om * u[0][1] + ec.x; xc[2] = om * u[0][2] + ec.y; xc[3] = om * u[0][3] + ec.y;
         float sw = 0.f, sz = 0.f;
 #pragma unroll
@@ -560,18 +573,16 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           const int o = o1 + (j >> 1) * p1;
           float ew = 0.f, ee = 0.f;
           if (act) {
-            ew = L1.E[o - 1];
-            ee = L1.E[o + 2];
+            ew = left ? 0.f : X1[o - 1];  // the wall is a face towards the value 0 (X1's guard ring is not zero)
+            ee = right ? 0.f : X1[o + 2];
           }
           // x2 of the row below: row j+1 of my patch (its aggregate row changes at even j+1) or the halo row
           float2 en = ec;
           if (j == 7) en = eS;
-          else if (j & 1) en = act ? *reinterpret_cast<const float2*>(L1.E + o + p1) : make_float2(0.f, 0.f);
+          else if (j & 1) en = act ? *reinterpret_cast<const float2*>(X1 + o + p1) : make_float2(0.f, 0.f);
           float ub[4];
-          if (j == 7) halo(false, ub);
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            if (j != 7) ub[i] = u[j == 7 ? 7 : j + 1][i];
+          for (int i = 0; i < 4; i++) ub[i] = j == 7 ? hS[i] : u[j == 7 ? 7 : j + 1][i];
           xn[0] = om * ub[0] + en.x; xn[1] = om * ub[1] + en.x; xn[2] = om * ub[2] + en.y; xn[3] = om * ub[3] + en.y;
           float uw = __shfl_up_sync(0xffffffffu, u[j][3], 1), ue = __shfl_down_sync(0xffffffffu, u[j][0], 1);
           if (left) uw = 0.f;
