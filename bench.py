@@ -215,9 +215,9 @@ def main():
     ok = bool((res["status"] == 0).all())
     # cell-updates (one evaluation of a cell's stencil row, operator or relaxation).  Per CG iteration the
     # on-chip multigrid kernel makes three passes over the image (A p, the restriction's residual, the
-    # post-smoothing sweep) and two over every coarse level (1/4 + 1/16 + 1/64 of the cells); the residual
-    # evaluations of the reliable updates are not counted (the kernel does not report how many it made).
-    PASSES = 3.0 + 2.0 * (1 / 4 + 1 / 16 + 1 / 64)
+    # post-smoothing sweep) and four over every coarse level (two sweeps per side; 1/4 + 1/16 + 1/64 of the cells);
+    # the residual evaluations of the reliable updates are not counted (the kernel does not report how many it made).
+    PASSES = 3.0 + 4.0 * (1 / 4 + 1 / 16 + 1 / 64)
     updates_per_step = float((iters * PASSES + 2).sum()) * cells
     k_ms = kernel_ms / args.steps
     peak, peak_kind = measured_peak()
@@ -252,7 +252,7 @@ def main():
         "roofline": {"kernel": "k_batch2d_mg", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("k_batch2d_mg", n_img), "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": 16.0 * updates_per_step,
-                     "note": "HBM-equivalent: 16 B x cell-updates / kernel time (3.66 stencil passes per CG iteration, see "
+                     "note": "HBM-equivalent: 16 B x cell-updates / kernel time (4.31 stencil passes per CG iteration, see "
                              "DESIGN 3).  The whole solve of an image runs inside one SM (shared memory, registers, an "
                              "L2-resident slice), so this kernel is issue/latency bound, not HBM bound -- its real DRAM "
                              "traffic is `traffic` -- and the figure is a work rate, not a bandwidth claim (SURVEY 8d, "
@@ -325,7 +325,11 @@ def main():
         out["cpu_baseline"] = {"value": k / tc, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": f"first {k} images of the batch, reference batch mode (OpenMP over images, "
                                          f"SerialGS each) at the shipped Convergence 1e-5; mean sweeps {ref[:, 3].mean():.0f}",
-                               "max_keff_gap_vs_gpu": float(np.max(np.abs(ref[:, 0] - res_h["keff"][:k]) / res_h["keff"][:k]))}
+                               "max_keff_gap_vs_gpu": float(np.max(np.abs(ref[:, 0] - res_h["keff"][:k]) / res_h["keff"][:k])),
+                               "gap_note": "the reference stops on its own loose test (Keff changed < 1e-5 between two checks), "
+                                           "1e-3..1e-2 away from the discrete solution on these images (SURVEY 8c); the GPU "
+                                           "results are at TRUE relative residual 1e-8.  Parity proper is tests/test_gpu_parity.py "
+                                           "(tight reference, Keff within 1e-5)"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -233,7 +233,7 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
         if (const char* e = getenv("KEFFB200_BATCH_WC")) sscanf(e, "%f,%f", &wc1, &wc2);
         wc_read = true;
       }
-      static const double delta2 = getenv("KEFFB200_BATCH_DELTA") ? atof(getenv("KEFFB200_BATCH_DELTA")) : 1e-5;
+      static const double delta2 = getenv("KEFFB200_BATCH_DELTA") ? atof(getenv("KEFFB200_BATCH_DELTA")) : 1e-4;
       k_batch2d_mg<<<grid, MB_THREADS, MB_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual, P.flux_balance,
                                                         (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, om, wc1, wc2, delta2,
                                                         ws, T, res + first, counters + slot);
@@ -303,6 +303,39 @@ static int batch2d_collect(const BatchWs& w, int n_img, const keffb200_params& P
   return 0;
 }
 
+// An on-chip mixed-precision solve that reports a breakdown (status 2: the FP32 recurrence left the positive
+// cone; seen with a reliable-update window of 1e-5 at conductivity ratios ~ 1e4) is re-solved by the all-FP64
+// kernel, so a caller never receives a field that did not converge without being told (status stays 1 or 2 only if
+// the FP64 solve fails as well).
+static int batch2d_rescue(const uint8_t* d_solid, int n_img, int nx, int ny, const keffb200_params& P, double* d_T_out,
+                          const BatchWs& w, keffb200_result* out) {
+  Ctx& c = ctx();
+  std::vector<int> bad;
+  for (int i = 0; i < n_img; i++)
+    if (out[i].status == 2 || !std::isfinite(out[i].keff)) bad.push_back(i);
+  if (bad.empty() || (P.flags & KEFFB200_F_BATCH_GLOBAL)) return 0;
+  keffb200_params Q = P;
+  Q.flags |= KEFFB200_F_BATCH_GLOBAL;
+  for (int i : bad) {
+    KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
+    KB_TRY(batch2d_enqueue(d_solid, i, 1, nx, ny, Q, d_T_out, w.ws, w.codes, w.res, w.counters, 0));
+  }
+  std::vector<BatchOut> h(n_img);
+  KB_CUDA(cudaMemcpyAsync(h.data(), w.res, (size_t)n_img * sizeof(BatchOut), cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  for (int i : bad) {
+    keffb200_result& o = out[i];
+    o.q_left = h[i].ql;
+    o.q_right = h[i].qr;
+    o.keff = (h[i].ql + h[i].qr) / 2 / (P.tr - P.tl);
+    o.rel_residual = h[i].bb > 0 ? sqrt(h[i].rr / h[i].bb) : 0.0;
+    o.energy_residual = h[i].r1;
+    o.iters += (long)h[i].it;
+    o.status = h[i].status;
+  }
+  return 0;
+}
+
 static int batch2d_check(int nx, int ny, const keffb200_params& P) {
   if (nx < 2 || ny < 2) return fail(KEFFB200_EINVAL, "image %dx%d too small", nx, ny);
   if (P.tr == P.tl) return fail(KEFFB200_EINVAL, "TR == TL: Keff undefined");
@@ -319,7 +352,8 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
   KB_CUDA(cudaEventRecord(c.ev0, c.st));
   KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
   KB_TRY(batch2d_enqueue(d_solid, 0, n_img, nx, ny, P, d_T_out, w.ws, w.codes, w.res, w.counters, 0));
-  return batch2d_collect(w, n_img, P, out);
+  KB_TRY(batch2d_collect(w, n_img, P, out));
+  return batch2d_rescue(d_solid, n_img, nx, ny, P, d_T_out, w, out);
 }
 
 // Host structures: the H2D copy runs on a second stream in three pieces (1/8, 3/8, 1/2 of the batch)
@@ -351,7 +385,8 @@ int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int 
     KB_CUDA(cudaStreamWaitEvent(c.st, c.evp[k], 0));
     KB_TRY(batch2d_enqueue(d_stage, first, count, nx, ny, P, d_T_out, w.ws, w.codes, w.res, w.counters, k));
   }
-  return batch2d_collect(w, n_img, P, out);
+  KB_TRY(batch2d_collect(w, n_img, P, out));
+  return batch2d_rescue(d_stage, n_img, nx, ny, P, d_T_out, w, out);
 }
 
 }  // namespace kb

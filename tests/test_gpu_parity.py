@@ -2,6 +2,8 @@
 fixtures.  Tolerances are BASELINE north_star's: Keff within 1e-5 relative of the tightly-converged
 reference, temperature within 1e-5 * |TR - TL| (the reference's own convergence tolerance).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -278,3 +280,24 @@ def test_batch_multigrid_kernel_contrast_and_flags(K):
     z = K.solve2d_batch(imgs, K.default_params(flags=K.F_ZERO_INIT))
     w = K.solve2d_batch(imgs)
     assert all(x["status"] == 0 and rel(x["keff"], y["keff"]) < 1e-6 for x, y in zip(z, w))
+
+
+def test_batch_breakdown_is_rescued_by_the_fp64_kernel():
+    """With a reliable-update window of 1e-5 the FP32 recurrence of the on-chip kernel breaks down on one of these
+    images (ks:kf = 15 000); the library must notice (status 2 inside) and hand that image to the all-FP64 kernel, so
+    every returned record is converged.  Own process: the window is read from the environment once."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, keff_cfd_b200 as K\n"
+        "from keff_cfd_b200 import structures as S\n"
+        "K.init(0); imgs = S.disc_images(8)\n"
+        "p = dict(ks=400.0, kf=0.026, tl=300.0, tr=290.0)\n"
+        "a = K.solve2d_batch(imgs, K.default_params(**p)); b = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_GLOBAL, **p))\n"
+        "assert (a['status'] == 0).all() and (a['rel_residual'] <= 1e-8).all(), (a['status'], a['rel_residual'])\n"
+        "assert (np.abs(a['keff'] - b['keff']) / np.abs(b['keff'])).max() < 1e-5\n"
+        "print('rescued ok', a['iters'])\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KEFFB200_BATCH_DELTA="1e-5", KEFFB200_BATCH_OMEGA="0.8")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "rescued ok" in r.stdout, r.stdout + r.stderr
