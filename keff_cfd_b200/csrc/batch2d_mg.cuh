@@ -418,31 +418,46 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       if (tid + nax < na) AI[tid * MB_NA + tid + nax] = AI[(tid + nax) * MB_NA + tid] = -cs;
     }
     __syncthreads();
-    // Gauss-Jordan without pivoting (SPD M-matrix), branch-free: with r = pivot row / pivot (r_k = 1 / pivot) and
-    // c = pivot column, every entry becomes (i == k ? r_j : (j == k ? 0 : A_ij) - c_i r_j).  Thread -> row tid / 8,
-    // columns (tid % 8) * 8 .. + 7 (two float4); rows / columns >= na hold zeros and stay zero.
+    // Gauss-Jordan without pivoting (SPD M-matrix), branch-free, ONE barrier per pivot: with r = pivot row / pivot
+    // (r_k = 1 / pivot) and c = pivot column, every entry becomes (i == k ? r_j : (j == k ? 0 : A_ij) - c_i r_j).
+    // Thread -> row tid / 8, columns (tid % 8) * 8 .. + 7 (two float4); the threads that have just produced row k+1
+    // and column k+1 publish them (unnormalised) in the other half of the scratch buffer for the next step.
+    // Rows / columns >= na hold zeros and stay zero.
     {
       const int gi = tid >> 3, gj = (tid & 7) * 8;
       float4* arow = reinterpret_cast<float4*>(AI + gi * MB_NA + gj);
+      if (tid < MB_NA) {
+        scr[tid] = AI[tid];               // row 0
+        scr[64 + tid] = AI[tid * MB_NA];  // column 0
+      }
+      __syncthreads();
       for (int k = 0; k < na; k++) {
-        if (tid < MB_NA) {
-          const float pinv = 1.f / AI[k * MB_NA + k];
-          scr[tid] = tid == k ? pinv : AI[k * MB_NA + tid] * pinv;  // r
-          scr[64 + tid] = AI[tid * MB_NA + k];                      // c
-        }
-        __syncthreads();
-        const float ci = scr[64 + gi];
-        const float4 r0 = *reinterpret_cast<const float4*>(scr + gj), r1 = *reinterpret_cast<const float4*>(scr + gj + 4);
+        const float* buf = scr + (k & 1) * 128;
+        float* nbuf = scr + ((k + 1) & 1) * 128;
+        const float pinv = 1.f / buf[k];
+        const float ci = buf[64 + gi];
+        const float4 r0 = *reinterpret_cast<const float4*>(buf + gj), r1 = *reinterpret_cast<const float4*>(buf + gj + 4);
         float4 a0 = arow[0], a1 = arow[1];
         const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
+          const float rj = gj + jj == k ? pinv : rr[jj] * pinv;
           const float keep = gj + jj == k ? 0.f : av[jj];
-          av[jj] = gi == k ? rr[jj] : keep - ci * rr[jj];
+          av[jj] = gi == k ? rj : keep - ci * rj;
         }
         arow[0] = make_float4(av[0], av[1], av[2], av[3]);
         arow[1] = make_float4(av[4], av[5], av[6], av[7]);
+        if (gi == k + 1) {
+          *reinterpret_cast<float4*>(nbuf + gj) = make_float4(av[0], av[1], av[2], av[3]);
+          *reinterpret_cast<float4*>(nbuf + gj + 4) = make_float4(av[4], av[5], av[6], av[7]);
+        }
+        if (k + 1 >= gj && k + 1 < gj + 8) {
+          float cv = av[0];
+#pragma unroll
+          for (int jj = 1; jj < 8; jj++) cv = gj + jj == k + 1 ? av[jj] : cv;
+          nbuf[64 + gi] = cv;
+        }
         __syncthreads();
       }
     }

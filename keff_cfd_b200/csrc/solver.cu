@@ -305,6 +305,8 @@ struct Mg {
   int grid = 0, gu = 0;        // CTAs of the stencil passes / of the row-wise vector kernels
   int nu = 2;                  // smoothing sweeps before and after the coarse correction
   float om[4] = {0.595f, 1.614f, 0.f, 0.f};  // their weights (Chebyshev points of [0.4, 1.9] for nu = 2)
+  int nu0 = 2;                 // the same for the voxel grid alone (KEFFB200_MG_OMEGA0 overrides; default = nu, om)
+  float om0[4] = {0.595f, 1.614f, 0.f, 0.f};
   Dom D{};
   Coef C{};
 };
@@ -343,6 +345,18 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       q = *end == ',' ? end + 1 : end;
     }
     if (k >= 1) mg.nu = k;
+  }
+  mg.nu0 = mg.nu;
+  for (int k = 0; k < 4; k++) mg.om0[k] = mg.om[k];
+  if (const char* e = getenv("KEFFB200_MG_OMEGA0")) {  // voxel grid: its own sweep count / weights (experiments)
+    int k = 0;
+    for (const char* q = e; *q && k < 4; k++) {
+      char* end = nullptr;
+      mg.om0[k] = strtof(q, &end);
+      if (end == q) break;
+      q = *end == ',' ? end + 1 : end;
+    }
+    if (k >= 1) mg.nu0 = k;
   }
   Nccl& nc = c.nccl;
   mg.dist = c.dist_active && nc.world > 1;
@@ -489,7 +503,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   mg.pitch = mg_pitch(D.nx);
   {
     const size_t uplane = (size_t)mg.pitch * D.ny, need = uplane * (D.nz + 2);
-    if (mg.nu >= 2 && need > c.cap_xf) {
+    if (mg.nu0 >= 2 && need > c.cap_xf) {
       for (int k = 0; k < 2; k++) {
         if (c.xf[k]) cudaFree(c.xf[k]);
         c.xf[k] = nullptr;
@@ -498,7 +512,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       for (int k = 0; k < 2; k++) KB_CUDA(cudaMalloc(&c.xf[k], need * sizeof(float)));
       c.cap_xf = need;
     }
-    float* fields[3] = {c.u, mg.nu >= 2 ? c.xf[0] : nullptr, mg.nu >= 2 ? c.xf[1] : nullptr};
+    float* fields[3] = {c.u, mg.nu0 >= 2 ? c.xf[0] : nullptr, mg.nu0 >= 2 ? c.xf[1] : nullptr};
     CUtensorMap* maps[3] = {&mg.tm_u, &mg.tm_x[0], &mg.tm_x[1]};
     for (int k = 0; k < 3; k++) {
       if (!fields[k]) continue;
@@ -603,15 +617,16 @@ static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass&
 // z-slabs: every array that a pass reads across a slab boundary has its halo planes exchanged first.
 static int mg_vcycle(const Mg& mg, float* z) {
   Ctx& c = ctx();
-  const int lo = mg.lo, hi = mg.hi, nu = mg.nu;
+  const int lo = mg.lo, hi = mg.hi, nu = mg.nu, nu0 = mg.nu0;
   const float* w = mg.om;
+  const float* w0 = mg.om0;
   KB_TRY(exchange_planes(c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
   // ---- voxel grid, down ----
   int cur = 0;  // field holding the current iterate (0 = u, scaled by w_1)
-  float sc = w[0];
-  for (int k = 1; k < nu; k++) {
+  float sc = w0[0];
+  for (int k = 1; k < nu0; k++) {
     const int out = cur == 1 ? 1 : 0;  // iterate fields alternate: u -> x0 -> x1 -> x0 ..
-    KB_TRY(mg_fine_pass(mg, cur, out, false, MgPass{sc, 1.f - w[k], w[k], w[k]}, z));
+    KB_TRY(mg_fine_pass(mg, cur, out, false, MgPass{sc, 1.f - w0[k], w0[k], w0[k]}, z));
     cur = out + 1;
     sc = 1.f;
   }
@@ -692,9 +707,9 @@ static int mg_vcycle(const Mg& mg, float* z) {
   // ---- voxel grid, up ----
   cur = fine_cur;
   sc = fine_sc;
-  for (int k = nu - 1; k >= 0; k--) {
+  for (int k = nu0 - 1; k >= 0; k--) {
     const int out = k == 0 ? -2 : (cur == 1 ? 1 : 0);
-    KB_TRY(mg_fine_pass(mg, cur, out, k == nu - 1, MgPass{sc, 1.f - w[k], w[k], w[k]}, z));
+    KB_TRY(mg_fine_pass(mg, cur, out, k == nu0 - 1, MgPass{sc, 1.f - w0[k], w0[k], w0[k]}, z));
     cur = out + 1;
     sc = 1.f;
   }
