@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's banner / debug lines (NCCL_DEBUG=VERSION prints "NCCL version ...") go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N_IMG, NPIX = 10000, 128
 METRIC, UNIT = "converged Keff solves/sec", "solves/s"
