@@ -340,12 +340,15 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
 // the ring keeps running across work items.  Stage layout: field box (BOXW x BOXH doubles, padded to
 // 128 B) followed by the TX x TY code bytes.
 // ------------------------------------------------------------------------------------------------
-constexpr int WS_NST = 6, WS_THR = NTHR + 32, WS_CODE_BYTES = TX * TY;
+#ifndef WS_OCC
+#define WS_OCC 2
+#endif
+constexpr int WS_NST = WS_OCC == 2 ? 9 : 6, WS_THR = NTHR + 32, WS_CODE_BYTES = TX * TY;
 constexpr int WS_STAGE = STAGE_STRIDE + WS_CODE_BYTES;
 constexpr int WS_SMEM = WS_NST * WS_STAGE + 128;
 
 template <int MODE>
-__global__ void __launch_bounds__(WS_THR, 3) k_stencil_ws(const __grid_constant__ CUtensorMap tm,
+__global__ void __launch_bounds__(WS_THR, WS_OCC) k_stencil_ws(const __grid_constant__ CUtensorMap tm,
                                                           const __grid_constant__ CUtensorMap tmc,
                                                           double* __restrict__ o0, double* __restrict__ o1,
                                                           const Coef C, const Dom D, const Plan P,

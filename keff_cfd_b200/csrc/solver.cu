@@ -217,7 +217,10 @@ static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
     KB_TRY(make_tmap(&s.tm_x, c.x, D));
     KB_TRY(make_tmap(&s.tm_p, c.p, D));
     // experiment switch: the warp-specialised ring (producer warp + full/empty mbarriers, code bytes by TMA).
-    // Measured at 512^3 on B200: 0.445 ms against 0.421 ms for the __syncthreads ring, so it is off by default.
+    // Measured at 512^3 on B200: 0.445 ms (3 CTAs/SM, 72 registers, 6 stages) / 0.433 ms (2 CTAs/SM, 9 stages)
+    // against 0.421 ms for the __syncthreads ring, so it is off by default.  Also measured and rejected: a 6-stage
+    // __syncthreads ring (no change: prefetch depth is not the limiter) and an even split of (tile, plane) runs
+    // over the grid (0.608 ms: x-adjacent tiles stop streaming the same DRAM rows at the same time).
     static const bool want_ws = getenv("KEFFB200_STENCIL_WS") != nullptr;
     s.ws = want_ws && D.nx % 16 == 0;
     int occ = occupancy_tma<MODE_APPLY>();
@@ -244,7 +247,7 @@ static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
       const int real_nzc = (D.nz + zlen - 1) / zlen;
       const long items = tiles * real_nzc;
       const long per_cta = (items + G - 1) / G;
-      const long cost = per_cta * (zlen + 2 + 6);  // +6: per-item pipeline fill/drain
+      const long cost = per_cta * (zlen + 2 + (s.ws ? 1 : 6));  // +6: per-item pipeline fill/drain (the ws ring runs on)
       if (best_cost < 0 || cost < best_cost) {
         best_cost = cost;
         best_nzc = real_nzc;
