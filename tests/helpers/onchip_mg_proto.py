@@ -1,0 +1,96 @@
+"""numpy restatement of the on-chip multigrid cycle of k_batch2d_mg (keff_cfd_b200/csrc/batch2d_mg.cuh): same
+hierarchy (2x2 aggregates, halved coarse conductances, dense 8x8-cell level), same sweeps (one weighted-Jacobi sweep
+per side on the image, two on the coarse levels), FP64 throughout.  Test infrastructure only: it documents the
+algorithm the kernel implements and lets the CPU suite check that the cycle is symmetric positive definite and how
+many CG iterations it needs; the kernel itself is checked against the oracle in tests/test_gpu_parity.py."""
+import numpy as np
+
+
+class Level:
+    def __init__(self, cx, cy, wall):
+        self.cx, self.cy, self.wall = cx, cy, wall          # faces towards x+1 (ny, nx-1) / y+1 (ny-1, nx); wall (ny, nx)
+        d = wall.copy()
+        d[:, :-1] += cx; d[:, 1:] += cx
+        d[:-1, :] += cy; d[1:, :] += cy
+        self.d = d
+
+    def offdiag(self, x):                                   # sum_f c_f x_nb
+        s = np.zeros_like(x)
+        s[:, :-1] += self.cx * x[:, 1:]; s[:, 1:] += self.cx * x[:, :-1]
+        s[:-1, :] += self.cy * x[1:, :]; s[1:, :] += self.cy * x[:-1, :]
+        return s
+
+    def apply(self, x):
+        return self.d * x - self.offdiag(x)
+
+    def coarsen(self):
+        ny, nx = self.d.shape
+        cx = 0.5 * (self.cx[0::2, 1::2] + self.cx[1::2, 1::2])[:, :nx // 2 - 1]
+        cy = 0.5 * (self.cy[1::2, 0::2] + self.cy[1::2, 1::2])[:ny // 2 - 1, :]
+        wall = 0.5 * (self.wall[0::2, 0::2] + self.wall[0::2, 1::2] + self.wall[1::2, 0::2] + self.wall[1::2, 1::2])
+        return Level(cx, cy, wall)
+
+
+def fine_level(solid, ks=10.0, kf=1.0):
+    """The reference's 2D discretisation (Keff2D/keff2D.h:482-582) on the unit square."""
+    ny, nx = solid.shape
+    K = np.where(solid == 1, ks, kf).astype(float)
+    dx, dy = 1.0 / nx, 1.0 / ny
+    hm = lambda a, b: 2 * a * b / (a + b)
+    cx = hm(K[:, :-1], K[:, 1:]) * dy / dx
+    cy = hm(K[:-1, :], K[1:, :]) * dx / dy
+    wall = np.zeros((ny, nx))
+    wall[:, 0] += K[:, 0] * dy / (dx / 2)
+    wall[:, -1] += K[:, -1] * dy / (dx / 2)
+    return Level(cx, cy, wall)
+
+
+def hierarchy(solid, ks=10.0, kf=1.0):
+    levels = [fine_level(solid, ks, kf)]
+    for _ in range(4):
+        levels.append(levels[-1].coarsen())
+    L = levels[-1]
+    n = L.d.size
+    A = np.zeros((n, n))
+    for i in range(n):
+        e = np.zeros(n); e[i] = 1
+        A[:, i] = L.apply(e.reshape(L.d.shape)).ravel()
+    return levels, np.linalg.inv(A)
+
+
+def restrict(r):
+    return r[0::2, 0::2] + r[0::2, 1::2] + r[1::2, 0::2] + r[1::2, 1::2]
+
+
+def prolong(e):
+    return np.repeat(np.repeat(e, 2, 0), 2, 1)
+
+
+def vcycle(levels, dense, b, l=0, om0=0.8, wc=(0.7, 1.4)):
+    L = levels[l]
+    if l == len(levels) - 1:
+        return (dense @ b.ravel()).reshape(b.shape)
+    w = (om0,) if l == 0 else wc
+    x = np.zeros_like(b)
+    for wk in w:
+        x = x + wk * (b - L.apply(x)) / L.d
+    x = x + prolong(vcycle(levels, dense, restrict(b - L.apply(x)), l + 1, om0, wc))
+    for wk in reversed(w):
+        x = x + wk * (b - L.apply(x)) / L.d
+    return x
+
+
+def pcg(solid, ks=10.0, kf=1.0, tol=1e-8, maxit=200, **kw):
+    levels, dense = hierarchy(solid, ks, kf)
+    L0 = levels[0]
+    ny, nx = solid.shape
+    b = np.zeros((ny, nx)); b[:, -1] = L0.wall[:, -1]          # TL = 0, TR = 1
+    x = np.tile((np.arange(nx) + 0.5) / nx, (ny, 1))
+    r = b - L0.apply(x); z = vcycle(levels, dense, r, **kw); p = z.copy(); rz = (r * z).sum(); bn = np.sqrt((b * b).sum())
+    for it in range(1, maxit + 1):
+        q = L0.apply(p); a = rz / (p * q).sum(); x += a * p; r -= a * q
+        if np.sqrt((r * r).sum()) <= tol * bn:
+            break
+        z = vcycle(levels, dense, r, **kw); rzn = (r * z).sum(); p = z + (rzn / rz) * p; rz = rzn
+    keff = 0.5 * ((L0.wall[:, 0] * x[:, 0]).sum() + (L0.wall[:, -1] * (1 - x[:, -1])).sum())
+    return keff, it, x
