@@ -3,31 +3,34 @@
 // Same outer scheme as batch2d_onchip.cuh (FP32 conjugate gradients on chip, FP64 entering through
 // reliable updates: x += y flushed in FP64, true residual b - A x recomputed in FP64 with the FP64
 // coefficients, every stop decision on FP64 quantities), but the preconditioner is one geometric
-// multigrid V(1,1)-cycle instead of D^-1 + a 64-unknown coarse correction: 18 iterations per
-// 128x128 image instead of 153.  The linear system is still exactly the reference's
+// multigrid V-cycle instead of D^-1 + a 64-unknown coarse correction: 12 iterations per 128x128
+// image instead of 153.  The linear system is still exactly the reference's
 // (DiscretizeMatrixCD2D, Keff2D/keff2D.h:482-582); the cycle only changes how fast CG gets there.
 // Replaces the reference batch loop Keff2D/keff2D.cpp:341-471 (SerialGS per image) for images
 // whose sides are multiples of 16 and <= 128; other shapes keep k_batch2d_onchip / k_batch2d_pcg.
+// The same arithmetic in numpy: tests/helpers/onchip_mg_proto.py (checked on the CPU against the oracle).
 //
 // Hierarchy (all FP32, all in shared memory): level 0 = the image (nx x ny), level l = 2x2
 // aggregates of level l-1, down to level 4 (<= 8x8 = 64 cells) which is solved with a dense inverse
 // (Gauss-Jordan in shared memory once per image).  Transfers are piecewise constant; a coarse face
 // conductance is HALF the sum of the two fine face conductances crossing it (the re-discretised
 // operator on a uniform medium -- same rule as mg.cuh), wall conductances likewise.
-// Cycle, per level with u = D^-1 b:   x1 = w u;   r1 = b - A x1 = (1-w) D u + w sum_f c_f u_nb;
-//   e = coarse(P^T r1);   x2 = x1 + P e;   out = x2 + w D^-1 (b - A x2) = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb
-// -- symmetric positive definite (same D and w on both sides), as CG needs.  x1 and x2 are never stored:
-// a pass reads u (and the coarser correction) of the neighbours and forms them on the fly.
+// Cycle on level 0 (one weighted-Jacobi sweep per side, weight w, u = D^-1 b):
+//   x1 = w u;   r1 = b - A x1 = (1-w) D u + w sum_f c_f u_nb;   e = coarse(P^T r1);   x2 = x1 + P e;
+//   out = x2 + w D^-1 (b - A x2) = (1-w) x2 + w u + w D^-1 sum_f c_f x2_nb
+// x1 and x2 are never stored: a pass reads u (and the coarser correction) of the neighbours and forms them on the
+// fly.  Levels 1..3 make TWO sweeps per side (weights w1, w2 down, w2, w1 up) around one stored iterate X (passes
+// A-D above mb_sweep).  Same weights mirrored on the way up -> the cycle is symmetric positive definite, as CG needs.
 //
 // Level 0 lives in REGISTERS: a thread owns a 4(x) x 8(y) patch (512 threads, lane -> x, warp -> y), W/E
-// neighbours come from warp shuffles, the rows above/below the patch from a 16 KB exchange buffer in
-// shared memory (each warp publishes its first and last row of u once per cycle).  a_P is the sum of
-// the face conductances that every pass selects from the code bytes anyway, so no 1/a_P array exists.
-// p keeps its guarded shared-memory image (the CG stencil reads neighbours from it); the FP32 vectors
-// y (solution increment) and z (preconditioned residual) are touched only cell-by-cell and stream through
-// a per-CTA slice of global memory that stays L2-resident (128 KB per SM).
-// Per iteration: 3 passes over the image (CG stencil, restrict, post-smoothing), 6 small passes over the
-// coarse levels, one dense 64x64 mat-vec, 12 barriers, one block reduction.
+// neighbours come from warp shuffles, the rows above/below the patch from 16 KB of exchange rows in
+// shared memory (each warp publishes its first and last row of u once per cycle; a thread copies the two rows it
+// needs into registers, after which the space serves as X1).  a_P is the sum of the face conductances that every
+// pass selects from the code bytes anyway, so no 1/a_P array exists.  p keeps its guarded shared-memory image (the
+// CG stencil reads neighbours from it); the FP32 vectors y (solution increment), z = M r and w = M A p are touched
+// only cell by cell and stream through a per-CTA slice of global memory that stays L2-resident (192 KB per SM).
+// Per iteration: 3 passes over the image (CG stencil, restriction, post-smoothing), 12 small passes over the
+// coarse levels, one dense 64x64 mat-vec, 18 barriers, one block reduction.
 #pragma once
 #include "batch2d_onchip.cuh"
 
