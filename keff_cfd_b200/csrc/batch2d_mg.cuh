@@ -52,8 +52,9 @@ static_assert(mb_n(1) >= 16 * 2 * 128, "X1 must cover the exchange rows");
 constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
 constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
 constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 16 * 8 + 64;
-// per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | x (n)
-__host__ __device__ constexpr size_t mb_ws_stride(size_t n) { return n + 3 * 8192; }
+// per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | p image (8320: 130 x 128 floats) | x (n)
+constexpr int MB_PG_DOUBLES = MB_ROWS * MB_PITCH / 2;
+__host__ __device__ constexpr size_t mb_ws_stride(size_t n) { return n + 3 * 8192 + MB_PG_DOUBLES; }
 
 struct Row5 {
   float cw, c01, c12, c23, ce;  // x faces of a 4-cell row: W of cell 0, 0|1, 1|2, 2|3, E of cell 3
@@ -313,8 +314,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   extern __shared__ __align__(16) unsigned char mb_smem[];
   float* SM = reinterpret_cast<float*>(mb_smem);
   float* P = SM + MB_F_P;
-  float* XCH = SM + MB_F_XCH;
-  float* X1 = XCH;  // iterates / final corrections of levels 1..3 (X1 overlays the exchange rows)
+  float* X1 = SM + MB_F_XCH;  // iterates / final corrections of levels 1..3
   float* X2 = SM + MB_F_X2;
   float* X3 = SM + MB_F_X3;
   float* LV = SM + MB_F_LV;
@@ -338,10 +338,14 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   const float om1 = 1.f - om;
 
   for (int i = tid; i < MB_F_END; i += MB_THREADS) SM[i] = 0.f;  // guard rings stay zero for the whole launch
-  float* Pown = P + (y0 + 1) * MB_PITCH + x0;
+  float* Uown = P + (y0 + 1) * MB_PITCH + x0;  // my patch's first row inside the guarded image of u
   // y, z, w slices: thread-major float4 rows at compile-time offsets from one base
   float4* Yg = reinterpret_cast<float4*>(xws + (size_t)blockIdx.x * mb_ws_stride(n)) + tid;
   constexpr int ZG = 8 * MB_THREADS, WG = 16 * MB_THREADS;  // z and w relative to y (in float4)
+  // p: guarded image [130][128] in the slice (the CG stencil reads the neighbours' rows from it); guard rows stay 0
+  float* Pg = reinterpret_cast<float*>(Yg - tid) + 24 * MB_THREADS * 4;
+  for (int i = tid; i < MB_ROWS * MB_PITCH; i += MB_THREADS) Pg[i] = 0.f;
+  float* Pown = Pg + (y0 + 1) * MB_PITCH + x0;
   // level-1 cells of my patch: aggregate rows (y0>>1) + 0..3, aggregate columns (x0>>1) + 0..1
   MbLv<1> L1(LV);
   MbLv<2> L2(LV);
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
     if (img >= n_img) break;
     const size_t moff = (size_t)img * n;
 #define MB_M (masks + moff)
-    double* x64 = T_out ? T_out + (size_t)img * n : reinterpret_cast<double*>(Yg - tid) + 3 * 8192;
+    double* x64 = T_out ? T_out + (size_t)img * n : reinterpret_cast<double*>(Yg - tid) + 3 * 8192 + MB_PG_DOUBLES;
 
     // ---- per-image setup: code words (registers), x = initial field, y = 0 ----
     unsigned cw[8];
@@ -465,52 +469,37 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
     }
 
-    // ---- the V-cycle: u (= D^-1 a, registers) -> w (registers); swq = sum w.a, szq = sum z.a over my patch ----
-    float u[8][4];
+    // ---- the V-cycle: u (= D^-1 a, in the shared-memory image U0) -> w (global slice `outg`);
+    //      swq = sum w.a, szq = sum z.a over my patch ----
     auto vcycle = [&](bool with_z, int outg, float& swq, float& szq) {
-      // publish my first and last row of u, then read the rows just above / below the patch
-      if (act) {
-        *reinterpret_cast<float4*>(XCH + (wrp * 2 + 0) * 128 + x0) = make_float4(u[0][0], u[0][1], u[0][2], u[0][3]);
-        *reinterpret_cast<float4*>(XCH + (wrp * 2 + 1) * 128 + x0) = make_float4(u[7][0], u[7][1], u[7][2], u[7][3]);
-      }
-      __syncthreads();
-      // u of the row just above / below my patch (zero outside the image); kept in registers for the post-smoothing
-      // pass because X1 overwrites the exchange rows in between
-      float hN[4] = {0.f, 0.f, 0.f, 0.f}, hS[4] = {0.f, 0.f, 0.f, 0.f};
-      if (act && !top) {
-        const float4 t = *reinterpret_cast<const float4*>(XCH + ((wrp - 1) * 2 + 1) * 128 + x0);
-        hN[0] = t.x; hN[1] = t.y; hN[2] = t.z; hN[3] = t.w;
-      }
-      if (act && !bot) {
-        const float4 t = *reinterpret_cast<const float4*>(XCH + ((wrp + 1) * 2) * 128 + x0);
-        hS[0] = t.x; hS[1] = t.y; hS[2] = t.z; hS[3] = t.w;
-      }
+      __syncthreads();  // every row of u is in the image
+      auto urow = [&](int j, float (&v)[4]) {  // row j of my patch (-1 and 8: the neighbours' rows or the zero guard rows)
+        const float4 t = *reinterpret_cast<const float4*>(Uown + j * MB_PITCH);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      };
       // ---- level 0, restriction: r1 = (1-w) d u + w sum_f c_f u_nb, summed over 2x2 aggregates ----
       {
         mb_fresh(cw);
-        float nn[4];
+        float nn[4], un[4], uc[4], us[4];
         mb_north(cw[0], F, top, nn);
+        urow(-1, un);
+        urow(0, uc);
         float a01 = 0.f, a23 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
+          urow(j + 1, us);
           const Row5 r = mb_row(cw[j], F, left, right, j == 7 && bot);
-          float uw = __shfl_up_sync(0xffffffffu, u[j][3], 1), ue = __shfl_down_sync(0xffffffffu, u[j][0], 1);
+          float uw = __shfl_up_sync(0xffffffffu, uc[3], 1), ue = __shfl_down_sync(0xffffffffu, uc[0], 1);
           if (left) uw = 0.f;
           if (right || lane == 31) ue = 0.f;
-          float un[4], us[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            un[i] = j == 0 ? hN[i] : u[j == 0 ? 0 : j - 1][i];
-            us[i] = j == 7 ? hS[i] : u[j == 7 ? 7 : j + 1][i];
-          }
           const float d0 = (r.cw + r.c01) + (nn[0] + r.s0), d1 = (r.c01 + r.c12) + (nn[1] + r.s1);
           const float d2 = (r.c12 + r.c23) + (nn[2] + r.s2), d3 = (r.c23 + r.ce) + (nn[3] + r.s3);
-          const float s0 = (r.cw * uw + r.c01 * u[j][1]) + (nn[0] * un[0] + r.s0 * us[0]);
-          const float s1 = (r.c01 * u[j][0] + r.c12 * u[j][2]) + (nn[1] * un[1] + r.s1 * us[1]);
-          const float s2 = (r.c12 * u[j][1] + r.c23 * u[j][3]) + (nn[2] * un[2] + r.s2 * us[2]);
-          const float s3 = (r.c23 * u[j][2] + r.ce * ue) + (nn[3] * un[3] + r.s3 * us[3]);
-          a01 += (om1 * d0 * u[j][0] + om * s0) + (om1 * d1 * u[j][1] + om * s1);
-          a23 += (om1 * d2 * u[j][2] + om * s2) + (om1 * d3 * u[j][3] + om * s3);
+          const float s0 = (r.cw * uw + r.c01 * uc[1]) + (nn[0] * un[0] + r.s0 * us[0]);
+          const float s1 = (r.c01 * uc[0] + r.c12 * uc[2]) + (nn[1] * un[1] + r.s1 * us[1]);
+          const float s2 = (r.c12 * uc[1] + r.c23 * uc[3]) + (nn[2] * un[2] + r.s2 * us[2]);
+          const float s3 = (r.c23 * uc[2] + r.ce * ue) + (nn[3] * un[3] + r.s3 * us[3]);
+          a01 += (om1 * d0 * uc[0] + om * s0) + (om1 * d1 * uc[1] + om * s1);
+          a23 += (om1 * d2 * uc[2] + om * s2) + (om1 * d3 * uc[3] + om * s3);
           if (j & 1) {
             if (act) {
               const int o = o1 + (j >> 1) * p1;
@@ -518,6 +507,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
               *reinterpret_cast<float2*>(L1.U + o) = make_float2(a01 * di.x, a23 * di.y);
             }
             a01 = a23 = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            un[i] = uc[i];
+            uc[i] = us[i];
           }
           nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
         }
@@ -582,8 +576,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         }
         float xp[4], xc[4], xn[4];  // x2 of the row above, this row, the row below
         float2 ec = act ? *reinterpret_cast<const float2*>(X1 + o1) : make_float2(0.f, 0.f);
-        xp[0] = om * hN[0] + eN.x; xp[1] = om * hN[1] + eN.x; xp[2] = om * hN[2] + eN.y; xp[3] = om * hN[3] + eN.y;
-        xc[0] = om * u[0][0] + ec.x; xc[1] = om * u[0][1] + ec.x; xc[2] = om * u[0][2] + ec.y; xc[3] = om * u[0][3] + ec.y;
+        float uc[4], ub[4];  // u of this row and of the row below
+        urow(-1, ub);
+        urow(0, uc);
+        xp[0] = om * ub[0] + eN.x; xp[1] = om * ub[1] + eN.x; xp[2] = om * ub[2] + eN.y; xp[3] = om * ub[3] + eN.y;
+        xc[0] = om * uc[0] + ec.x; xc[1] = om * uc[1] + ec.x; xc[2] = om * uc[2] + ec.y; xc[3] = om * uc[3] + ec.y;
         float sw = 0.f, sz = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -598,11 +595,9 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           float2 en = ec;
           if (j == 7) en = eS;
           else if (j & 1) en = act ? *reinterpret_cast<const float2*>(X1 + o + p1) : make_float2(0.f, 0.f);
-          float ub[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) ub[i] = j == 7 ? hS[i] : u[j == 7 ? 7 : j + 1][i];
+          urow(j + 1, ub);
           xn[0] = om * ub[0] + en.x; xn[1] = om * ub[1] + en.x; xn[2] = om * ub[2] + en.y; xn[3] = om * ub[3] + en.y;
-          float uw = __shfl_up_sync(0xffffffffu, u[j][3], 1), ue = __shfl_down_sync(0xffffffffu, u[j][0], 1);
+          float uw = __shfl_up_sync(0xffffffffu, uc[3], 1), ue = __shfl_down_sync(0xffffffffu, uc[0], 1);
           if (left) uw = 0.f;
           if (right || lane == 31) ue = 0.f;
           const float xw = om * uw + ew, xe = om * ue + ee;
@@ -613,13 +608,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           const float s2 = (r.c12 * xc[1] + r.c23 * xc[3]) + (nn[2] * xp[2] + r.s2 * xn[2]);
           const float s3 = (r.c23 * xc[2] + r.ce * xe) + (nn[3] * xp[3] + r.s3 * xn[3]);
           float4 wv;
-          wv.x = om1 * xc[0] + om * u[j][0] + om * __fdividef(s0, d0);
-          wv.y = om1 * xc[1] + om * u[j][1] + om * __fdividef(s1, d1);
-          wv.z = om1 * xc[2] + om * u[j][2] + om * __fdividef(s2, d2);
-          wv.w = om1 * xc[3] + om * u[j][3] + om * __fdividef(s3, d3);
+          wv.x = om1 * xc[0] + om * uc[0] + om * __fdividef(s0, d0);
+          wv.y = om1 * xc[1] + om * uc[1] + om * __fdividef(s1, d1);
+          wv.z = om1 * xc[2] + om * uc[2] + om * __fdividef(s2, d2);
+          wv.w = om1 * xc[3] + om * uc[3] + om * __fdividef(s3, d3);
           if (!act) wv = make_float4(0.f, 0.f, 0.f, 0.f);
           Yg[outg + j * MB_THREADS] = wv;
-          const float q0 = d0 * u[j][0], q1 = d1 * u[j][1], q2 = d2 * u[j][2], q3 = d3 * u[j][3];  // a = D u
+          const float q0 = d0 * uc[0], q1 = d1 * uc[1], q2 = d2 * uc[2], q3 = d3 * uc[3];  // a = D u
           sw += (wv.x * q0 + wv.y * q1) + (wv.z * q2 + wv.w * q3);
           if (with_z) {
             const float4 zv = Yg[ZG + j * MB_THREADS];
@@ -629,6 +624,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           for (int i = 0; i < 4; i++) {
             xp[i] = xc[i];
             xc[i] = xn[i];
+            uc[i] = ub[i];
           }
           ec = en;
           nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
@@ -714,9 +710,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
                                 (f23 - f12) + (nd[2] * (xn[2] - xc[2]) + rd.s2 * (xs[2] - xc[2])),
                                 (rd.ce * (xe - xc[3]) - f23) + (nd[3] * (xn[3] - xc[3]) + rd.s3 * (xs[3] - xc[3]))};
           const double b0 = left ? rd.cw * C.tl : 0.0, b3 = right ? rd.ce * C.tr : 0.0;  // right-hand side entries
+          *reinterpret_cast<float4*>(Uown + j * MB_PITCH) =
+              make_float4(__fdividef((float)rv[0], dd[0]), __fdividef((float)rv[1], dd[1]), __fdividef((float)rv[2], dd[2]),
+                          __fdividef((float)rv[3], dd[3]));
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            u[j][i] = __fdividef((float)rv[i], dd[i]);
             s4[1] += rv[i] * rv[i];
             s4[3] += fabs(rv[i]);
             xn[i] = xc[i];
@@ -726,11 +724,6 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
           nd[0] = rd.s0; nd[1] = rd.s1; nd[2] = rd.s2; nd[3] = rd.s3;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-#pragma unroll
-          for (int i = 0; i < 4; i++) u[j][i] = 0.f;
       }
       block_allsum<4>(s4, red, bc);
       S_rr_true = s4[1];
@@ -790,11 +783,15 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           mb_fresh(cw);
           float nn[4];
           mb_north(cw[0], F, top, nn);
-          float4 hn = *reinterpret_cast<const float4*>(Pown - MB_PITCH);
-          float4 pc = *reinterpret_cast<const float4*>(Pown);
+          // all ten rows of p first (L2 round trips in flight together); rows -1 and 8 are the neighbours' or zero guards
+          float4 prow[10];
+#pragma unroll
+          for (int j = 0; j < 10; j++) prow[j] = __ldcg(reinterpret_cast<const float4*>(Pown + (j - 1) * MB_PITCH));
+          float4 hn = prow[0];
+          float4 pc = prow[1];
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            const float4 pn = *reinterpret_cast<const float4*>(Pown + (j + 1) * MB_PITCH);
+            const float4 pn = prow[j + 2];
             float pw = __shfl_up_sync(0xffffffffu, pc.w, 1), pe = __shfl_down_sync(0xffffffffu, pc.x, 1);
             if (left) pw = 0.f;
             if (right || lane == 31) pe = 0.f;
@@ -806,20 +803,15 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
             const float q3 = (r.ce * (pc.w - pe) - f23) + (nn[3] * (pc.w - hn.w) + r.s3 * (pc.w - pn.w));
             const float d0 = (r.cw + r.c01) + (nn[0] + r.s0), d1 = (r.c01 + r.c12) + (nn[1] + r.s1);
             const float d2 = (r.c12 + r.c23) + (nn[2] + r.s2), d3 = (r.c23 + r.ce) + (nn[3] + r.s3);
-            u[j][0] = __fdividef(q0, d0); u[j][1] = __fdividef(q1, d1); u[j][2] = __fdividef(q2, d2);
-            u[j][3] = __fdividef(q3, d3);
+            if (act)
+              *reinterpret_cast<float4*>(Uown + j * MB_PITCH) =
+                  make_float4(__fdividef(q0, d0), __fdividef(q1, d1), __fdividef(q2, d2), __fdividef(q3, d3));
             spq += (pc.x * q0 + pc.y * q1) + (pc.z * q2 + pc.w * q3);
             nn[0] = r.s0; nn[1] = r.s1; nn[2] = r.s2; nn[3] = r.s3;
             hn = pc;
             pc = pn;
           }
-          if (!act) {
-            spq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-#pragma unroll
-              for (int i = 0; i < 4; i++) u[j][i] = 0.f;
-          }
+          if (!act) spq = 0.f;
         }
         vcycle(true, WG, swq, szq);  // w = M q (into its slice), sums w.q and z.q
         // one barrier per reduction: FP32 inside a warp, FP64 across the 16 warps, every warp sums the 16
@@ -864,7 +856,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         it++;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          float4 pv = *reinterpret_cast<const float4*>(Pown + j * MB_PITCH);
+          float4 pv = __ldcg(reinterpret_cast<const float4*>(Pown + j * MB_PITCH));
           float4 yv = Yg[j * MB_THREADS];
           float4 zv = Yg[ZG + j * MB_THREADS];
           const float4 wv = Yg[WG + j * MB_THREADS];
