@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
 
     // ---- the V-cycle: u (= D^-1 a, in the shared-memory image U0) -> w (global slice `outg`);
     //      swq = sum w.a, szq = sum z.a over my patch ----
-    auto vcycle = [&](bool with_z, int outg, float& swq, float& szq) {
+    float w[8][4];
+    auto vcycle = [&](bool with_z, float& swq, float& szq) {
       __syncthreads();  // every row of u is in the image
       auto urow = [&](int j, float (&v)[4]) {  // row j of my patch (-1 and 8: the neighbours' rows or the zero guard rows)
         const float4 t = *reinterpret_cast<const float4*>(Uown + j * MB_PITCH);
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           wv.z = om1 * xc[2] + om * uc[2] + om * __fdividef(s2, d2);
           wv.w = om1 * xc[3] + om * uc[3] + om * __fdividef(s3, d3);
           if (!act) wv = make_float4(0.f, 0.f, 0.f, 0.f);
-          Yg[outg + j * MB_THREADS] = wv;
+          w[j][0] = wv.x; w[j][1] = wv.y; w[j][2] = wv.z; w[j][3] = wv.w;
           const float q0 = d0 * uc[0], q1 = d1 * uc[1], q2 = d2 * uc[2], q3 = d3 * uc[3];  // a = D u
           sw += (wv.x * q0 + wv.y * q1) + (wv.z * q2 + wv.w * q3);
           if (with_z) {
@@ -757,7 +758,9 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
       {  // z = M r straight into its slice; r.z with r rounded to FP32
         float swq, szq;
-        vcycle(false, ZG, swq, szq);
+        vcycle(false, swq, szq);
+#pragma unroll
+        for (int j = 0; j < 8; j++) Yg[ZG + j * MB_THREADS] = make_float4(w[j][0], w[j][1], w[j][2], w[j][3]);
         double s1[1] = {(double)swq};
         block_allsum<1>(s1, red, bc);
         rz = s1[0];
@@ -767,7 +770,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       if (first || restart || fresh_p) {  // p = z (start, or restart after a window that did not reach its target)
         if (act)
 #pragma unroll
-          for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = Yg[ZG + j * MB_THREADS];
+          for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(Pown + j * MB_PITCH) = make_float4(w[j][0], w[j][1], w[j][2], w[j][3]);
         first = false;
         restart = false;
         fresh_p = false;
@@ -813,7 +816,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           }
           if (!act) spq = 0.f;
         }
-        vcycle(true, WG, swq, szq);  // w = M q (into its slice), sums w.q and z.q
+        vcycle(true, swq, szq);  // w = M q (registers), sums w.q and z.q
         // one barrier per reduction: FP32 inside a warp, FP64 across the 16 warps, every warp sums the 16
         // partials itself (fixed order -> deterministic); `red` is double-buffered by parity
         double s3[3];
@@ -859,8 +862,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
           float4 pv = __ldcg(reinterpret_cast<const float4*>(Pown + j * MB_PITCH));
           float4 yv = Yg[j * MB_THREADS];
           float4 zv = Yg[ZG + j * MB_THREADS];
-          const float4 wv = Yg[WG + j * MB_THREADS];
-          zv.x -= al * wv.x; zv.y -= al * wv.y; zv.z -= al * wv.z; zv.w -= al * wv.w;
+          zv.x -= al * w[j][0]; zv.y -= al * w[j][1]; zv.z -= al * w[j][2]; zv.w -= al * w[j][3];
           yv.x += al * pv.x; yv.y += al * pv.y; yv.z += al * pv.z; yv.w += al * pv.w;
           pv.x = zv.x + be * pv.x; pv.y = zv.y + be * pv.y; pv.z = zv.z + be * pv.z; pv.w = zv.w + be * pv.w;
           Yg[j * MB_THREADS] = yv;
