@@ -22,13 +22,14 @@
 // fly.  Levels 1..3 make TWO sweeps per side (weights w1, w2 down, w2, w1 up) around one stored iterate X (passes
 // A-D above mb_sweep).  Same weights mirrored on the way up -> the cycle is symmetric positive definite, as CG needs.
 //
-// Level 0 lives in REGISTERS: a thread owns a 4(x) x 8(y) patch (512 threads, lane -> x, warp -> y), W/E
-// neighbours come from warp shuffles, the rows above/below the patch from 16 KB of exchange rows in
-// shared memory (each warp publishes its first and last row of u once per cycle; a thread copies the two rows it
-// needs into registers, after which the space serves as X1).  a_P is the sum of the face conductances that every
-// pass selects from the code bytes anyway, so no 1/a_P array exists.  p keeps its guarded shared-memory image (the
-// CG stencil reads neighbours from it); the FP32 vectors y (solution increment), z = M r and w = M A p are touched
-// only cell by cell and stream through a per-CTA slice of global memory that stays L2-resident (192 KB per SM).
+// Level 0: a thread owns a 4(x) x 8(y) patch (512 threads, lane -> x, warp -> y).  u = D^-1 a lives in a guarded
+// shared-memory image (written by the CG stencil / the reliable update, read row by row with LDS.128 by the
+// restriction and post-smoothing passes; W/E neighbours come from warp shuffles, the rows above/below the patch are
+// the neighbour warps' rows of the image).  Keeping u in registers instead (first light) cost 584 B of spills per
+// thread.  a_P is the sum of the face conductances that every pass selects from the code bytes anyway, so no 1/a_P
+// array exists.  w = M A p stays in registers from the post-smoothing pass to the vector update.  p (a guarded image:
+// the CG stencil reads the neighbours' rows with ld.global.cg), y (solution increment) and z = M r are touched once
+// or twice per iteration and stream through a per-CTA slice of global memory that stays L2-resident (200 KB per SM).
 // Per iteration: 3 passes over the image (CG stencil, restriction, post-smoothing), 12 small passes over the
 // coarse levels, one dense 64x64 mat-vec, 18 barriers, one block reduction.
 #pragma once
@@ -42,13 +43,10 @@ __host__ __device__ constexpr int mb_pitch(int L) { return (128 >> L) + 4; }
 __host__ __device__ constexpr int mb_rows(int L) { return (128 >> L) + 2; }
 __host__ __device__ constexpr int mb_n(int L) { return mb_pitch(L) * mb_rows(L); }
 __host__ __device__ constexpr int mb_off(int L) { return L <= 1 ? 0 : mb_off(L - 1) + 5 * mb_n(L - 1); }
-// floats: p image | exchange rows = X1 | X2 | X3 | levels 1..3 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
+// floats: u image | X1 | X2 | X3 | levels 1..3 (U, E, CX, CY, DI each) | dense-level correction (guarded) |
 //         dense right-hand side | dense inverse | scratch
-// The iterates X of levels 1..3 start at the exchange rows: X1 overlays them (they are dead once every thread holds
-// its halo rows in registers, and X1 is dead again when the next cycle publishes new rows).
 constexpr int MB_F_P = 0, MB_F_XCH = MB_F_P + MB_ROWS * MB_PITCH, MB_F_X2 = MB_F_XCH + mb_n(1), MB_F_X3 = MB_F_X2 + mb_n(2);
 constexpr int MB_F_LV = MB_F_X3 + mb_n(3);
-static_assert(mb_n(1) >= 16 * 2 * 128, "X1 must cover the exchange rows");
 constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
 constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
 constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 16 * 8 + 64;
