@@ -356,7 +356,7 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
   return batch2d_rescue(d_solid, n_img, nx, ny, P, d_T_out, w, out);
 }
 
-// Host structures: the H2D copy runs on a second stream in three pieces (1/8, 3/8, 1/2 of the batch)
+// Host structures: the H2D copy runs on a second stream in three pieces (1/16, 3/16, 3/4 of the batch)
 // and each piece's solve waits only for its own copy, so all but the first 1/8 of the transfer hides
 // behind compute.  d_stage: device staging buffer for the whole batch.
 int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int nx, int ny, const keffb200_params& P,
@@ -366,8 +366,10 @@ int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int 
   BatchWs w;
   KB_TRY(batch2d_workspace(n_img, nx, ny, w));
   const size_t n = (size_t)nx * ny;
-  int cut[4] = {0, n_img / 8, n_img / 2, n_img};
-  if (n_img < 4 * c.sms) cut[1] = cut[2] = 0;  // small batches: one piece
+  // pieces of 1/16, 3/16 and 3/4 of the batch: only the first copy (1/16) is exposed, and every later copy is
+  // shorter than the compute it hides behind (a 128x128 image takes ~6x longer to solve than to copy)
+  int cut[4] = {0, n_img / 16, n_img / 4, n_img};
+  if (n_img < 8 * c.sms) cut[1] = cut[2] = 0;  // small batches: one piece
   KB_CUDA(cudaEventRecord(c.ev0, c.st));
   KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
   KB_CUDA(cudaEventRecord(c.evx, c.st));
