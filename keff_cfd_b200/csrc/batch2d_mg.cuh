@@ -8,7 +8,7 @@
 // (DiscretizeMatrixCD2D, Keff2D/keff2D.h:482-582); the cycle only changes how fast CG gets there.
 // Replaces the reference batch loop Keff2D/keff2D.cpp:341-471 (SerialGS per image) for images
 // whose sides are multiples of 16 and <= 128; other shapes keep k_batch2d_onchip / k_batch2d_pcg.
-// The same arithmetic in numpy: tests/helpers/onchip_mg_proto.py (checked on the CPU against the oracle).
+// The same arithmetic in numpy: tests/helpers/onchip_mg_proto.py (checked on the CPU by tests/test_onchip_mg_design.py).
 //
 // Hierarchy (all FP32, all in shared memory): level 0 = the image (nx x ny), level l = 2x2
 // aggregates of level l-1, down to level 4 (<= 8x8 = 64 cells) which is solved with a dense inverse
