@@ -50,9 +50,9 @@ constexpr int MB_F_LV = MB_F_X3 + mb_n(3);
 constexpr int MB_F_E4 = MB_F_LV + mb_off(4), MB_F_B4 = MB_F_E4 + mb_n(4), MB_F_AI = MB_F_B4 + MB_NA;
 constexpr int MB_F_SCR = MB_F_AI + MB_NA * MB_NA, MB_F_END = MB_F_SCR + 256;
 constexpr size_t MB_SMEM = (size_t)MB_F_END * 4 + 2 * 64 * 8 + 4 * 8 + 16 * 8 + 64;
-// per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | w (8192) | p image (8320: 130 x 128 floats) | x (n)
+// per-CTA global scratch (doubles): y (8192: 8 x 512 float4) | z (8192) | p image (8320: 130 x 128 floats) | x (n)
 constexpr int MB_PG_DOUBLES = MB_ROWS * MB_PITCH / 2;
-__host__ __device__ constexpr size_t mb_ws_stride(size_t n) { return n + 3 * 8192 + MB_PG_DOUBLES; }
+__host__ __device__ constexpr size_t mb_ws_stride(size_t n) { return n + 2 * 8192 + MB_PG_DOUBLES; }
 
 struct Row5 {
   float cw, c01, c12, c23, ce;  // x faces of a 4-cell row: W of cell 0, 0|1, 1|2, 2|3, E of cell 3
@@ -337,11 +337,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
 
   for (int i = tid; i < MB_F_END; i += MB_THREADS) SM[i] = 0.f;  // guard rings stay zero for the whole launch
   float* Uown = P + (y0 + 1) * MB_PITCH + x0;  // my patch's first row inside the guarded image of u
-  // y, z, w slices: thread-major float4 rows at compile-time offsets from one base
+  // y and z slices: thread-major float4 rows at compile-time offsets from one base
   float4* Yg = reinterpret_cast<float4*>(xws + (size_t)blockIdx.x * mb_ws_stride(n)) + tid;
-  constexpr int ZG = 8 * MB_THREADS, WG = 16 * MB_THREADS;  // z and w relative to y (in float4)
+  constexpr int ZG = 8 * MB_THREADS;  // z relative to y (in float4)
   // p: guarded image [130][128] in the slice (the CG stencil reads the neighbours' rows from it); guard rows stay 0
-  float* Pg = reinterpret_cast<float*>(Yg - tid) + 24 * MB_THREADS * 4;
+  float* Pg = reinterpret_cast<float*>(Yg - tid) + 16 * MB_THREADS * 4;
   for (int i = tid; i < MB_ROWS * MB_PITCH; i += MB_THREADS) Pg[i] = 0.f;
   float* Pown = Pg + (y0 + 1) * MB_PITCH + x0;
   // level-1 cells of my patch: aggregate rows (y0>>1) + 0..3, aggregate columns (x0>>1) + 0..1
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
     if (img >= n_img) break;
     const size_t moff = (size_t)img * n;
 #define MB_M (masks + moff)
-    double* x64 = T_out ? T_out + (size_t)img * n : reinterpret_cast<double*>(Yg - tid) + 3 * 8192 + MB_PG_DOUBLES;
+    double* x64 = T_out ? T_out + (size_t)img * n : reinterpret_cast<double*>(Yg - tid) + 2 * 8192 + MB_PG_DOUBLES;
 
     // ---- per-image setup: code words (registers), x = initial field, y = 0 ----
     unsigned cw[8];
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       }
     }
 
-    // ---- the V-cycle: u (= D^-1 a, in the shared-memory image U0) -> w (global slice `outg`);
+    // ---- the V-cycle: u (= D^-1 a, in the shared-memory image U0) -> w (registers);
     //      swq = sum w.a, szq = sum z.a over my patch ----
     float w[8][4];
     auto vcycle = [&](bool with_z, float& swq, float& szq) {
