@@ -243,7 +243,9 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
                                                           (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, T, res + first,
                                                           counters + slot);
   } else {
-    k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(m, count, nx, ny, C, P.rel_residual * P.rel_residual, P.flux_balance,
+    // diagonally preconditioned CG leaves its error in the smooth modes: at ks:kf = 300 a relative residual of 1e-8
+    // was seen 5e-5 away from the direct solution in Keff, so this kernel aims 100x lower than asked
+    k_batch2d_pcg<<<grid, 1024, 0, c.st>>>(m, count, nx, ny, C, 1e-4 * P.rel_residual * P.rel_residual, P.flux_balance,
                                            (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, ws, codes, T,
                                            res + first, counters + slot);
   }

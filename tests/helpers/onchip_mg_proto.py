@@ -94,3 +94,24 @@ def pcg(solid, ks=10.0, kf=1.0, tol=1e-8, maxit=200, **kw):
         z = vcycle(levels, dense, r, **kw); rzn = (r * z).sum(); p = z + (rzn / rz) * p; rz = rzn
     keff = 0.5 * ((L0.wall[:, 0] * x[:, 0]).sum() + (L0.wall[:, -1] * (1 - x[:, -1])).sum())
     return keff, it, x
+
+
+def direct_keff(solid, ks=10.0, kf=1.0, tl=0.0, tr=1.0):
+    """Keff from a sparse direct solve (scipy, FP64) of the same linear system: an answer that owes nothing to any of
+    the iterative solvers or their stop rules."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    L = fine_level(solid, ks, kf)
+    ny, nx = solid.shape
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    rows = [idx.ravel(), idx[:, :-1].ravel(), idx[:, 1:].ravel(), idx[:-1, :].ravel(), idx[1:, :].ravel()]
+    cols = [idx.ravel(), idx[:, 1:].ravel(), idx[:, :-1].ravel(), idx[1:, :].ravel(), idx[:-1, :].ravel()]
+    vals = [L.d.ravel(), -L.cx.ravel(), -L.cx.ravel(), -L.cy.ravel(), -L.cy.ravel()]
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nx * ny, nx * ny))
+    b = np.zeros((ny, nx))
+    b[:, 0] += tl * L.wall[:, 0]
+    b[:, -1] += tr * L.wall[:, -1]
+    T = sla.spsolve(A, b.ravel()).reshape(ny, nx)
+    ql = (L.wall[:, 0] * (T[:, 0] - tl)).sum()
+    qr = (L.wall[:, -1] * (tr - T[:, -1])).sum()
+    return (ql + qr) / 2 / (tr - tl)

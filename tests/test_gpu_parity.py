@@ -301,3 +301,26 @@ def test_batch_breakdown_is_rescued_by_the_fp64_kernel():
     env = dict(os.environ, KEFFB200_BATCH_DELTA="1e-5", KEFFB200_BATCH_OMEGA="0.8")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "rescued ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_batch_kernels_against_direct_solves_at_high_contrast(K):
+    """ks:kf = 300 on random and disc structures (96 x 112): a relative residual says little about Keff when the system
+    is this ill-conditioned, so the answers are compared with a sparse direct solve of the same system."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    import onchip_mg_proto as P
+    from keff_cfd_b200 import structures as S
+    rng = np.random.default_rng(42)
+    ny, nx = 96, 112
+    imgs = np.concatenate([(rng.random((3, ny, nx)) < p).astype(np.uint8) for p in (0.2, 0.5, 0.8)] +
+                          [S.disc_images(3, 128)[:, :ny, :nx]])
+    p = dict(ks=300.0, kf=1.0, tl=1.0, tr=3.0)
+    want = np.array([P.direct_keff(im, **p) for im in imgs])
+    mg = K.solve2d_batch(imgs, K.default_params(**p))
+    fp64 = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_GLOBAL, **p))
+    add = K.solve2d_batch(imgs, K.default_params(flags=K.F_BATCH_ADDITIVE, **p))
+    for r in (mg, fp64, add):
+        assert (r["status"] == 0).all()
+    assert (np.abs(mg["keff"] - want) <= 2e-6 * want).all()          # measured 7e-7
+    assert (np.abs(fp64["keff"] - want) <= 1e-5 * want).all()
+    assert (np.abs(add["keff"] - want) <= 1e-5 * want).all()
