@@ -44,3 +44,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "gpu":
         print(f"rel_residual {tolr}: mg", np.abs(a["keff"] - ref).max() / ref.max(), "fp64", (np.abs(b["keff"] - ref) / ref).max())
 else:
     print(ref)
+if len(sys.argv) > 1 and sys.argv[1] == "gpu":
+    g = np.array([K.solve2d(im, K.default_params(**p), want_T=False)["keff"] for im in imgs])
+    gj = np.array([K.solve2d(im, K.default_params(flags=K.F_NO_MG, **p), want_T=False)["keff"] for im in imgs])
+    print("grid solver (multigrid-PCG) gap vs direct", (np.abs(g - ref) / ref).max(), "| Jacobi-PCG fallback", (np.abs(gj - ref) / ref).max())
+    vol = np.stack([imgs[0], imgs[3], imgs[6], imgs[9]])          # a 4-plane 3D volume, direct solve too big: compare the two paths
+    a3 = K.solve3d(vol, K.default_params(**p), want_T=False); b3 = K.solve3d(vol, K.default_params(flags=K.F_NO_MG, **p), want_T=False)
+    print("3D 4x96x112: mg", a3["keff"], a3["iters"], "jacobi", b3["keff"], b3["iters"], "gap", abs(a3["keff"] - b3["keff"]) / b3["keff"])

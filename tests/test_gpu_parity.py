@@ -324,3 +324,9 @@ def test_batch_kernels_against_direct_solves_at_high_contrast(K):
     assert (np.abs(mg["keff"] - want) <= 2e-6 * want).all()          # measured 7e-7
     assert (np.abs(fp64["keff"] - want) <= 1e-5 * want).all()
     assert (np.abs(add["keff"] - want) <= 1e-5 * want).all()
+    # the grid solver on the same systems: multigrid-preconditioned path and the diagonally preconditioned fallback
+    for i in (0, 3, 6):
+        g = K.solve2d(imgs[i], K.default_params(**p), want_T=False)
+        j = K.solve2d(imgs[i], K.default_params(flags=K.F_NO_MG, **p), want_T=False)
+        assert g["status"] == 0 and abs(g["keff"] - want[i]) <= 2e-6 * want[i]
+        assert j["status"] == 0 and abs(j["keff"] - want[i]) <= 1e-5 * want[i]
