@@ -141,6 +141,11 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout must carry exactly ONE JSON line: whatever the libraries print while the job runs (NCCL's version
+    # banner, for one) goes to stderr; the real stdout is restored for the result line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -332,8 +337,11 @@ def main():
                                            "1e-3..1e-2 away from the discrete solution on these images (SURVEY 8c); the GPU "
                                            "results are at TRUE relative residual 1e-8.  Parity proper is tests/test_gpu_parity.py "
                                            "(tight reference, Keff within 1e-5)"}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    os.dup2(2, 1)  # anything printed during teardown goes to stderr again
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
