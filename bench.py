@@ -129,6 +129,65 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def KD_image_shard(n_img, rank, world):
+    from keff_cfd_b200 import dist as KD
+    return KD.image_shard(n_img, rank, world)
+
+
+def cpu_other_configs(refbind, api, p):
+    """The reference CPU code on the configs it can run besides the batch, bounded:
+    configs[0] = the shipped 00009.jpg at the shipped keys on one thread (deterministic), with the GPU solve of the
+    same image beside it; configs[2] = a fixed number of ParallelGS3D sweeps on the shipped-size Schwarz volume."""
+    out = {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    try:
+        img = np.load(os.path.join(gold, "img_00009.npy"))
+        if refbind.have_ref():
+            t0 = time.perf_counter()
+            r = refbind.ref2d_solve(img, tol=1e-5, threads=1, want_T=False)
+            tc = time.perf_counter() - t0
+            kind = "reference"
+        else:
+            t0 = time.perf_counter()
+            r = refbind.orc_solve2d(img, tol=1e-5)
+            tc = time.perf_counter() - t0
+            kind = "port"
+        solid = api.structure_from_image(img)
+        api.solve2d(solid, p, want_T=False)
+        g = api.solve2d(solid, p, want_T=False)
+        out["config0_00009"] = {"kind": kind, "cores": 1, "cpu_seconds": tc, "cpu_sweeps": int(r["iters"]), "cpu_keff": float(r["keff"]),
+                                "cpu_mcell_updates_per_s": r["iters"] * img.size / tc / 1e6, "gpu_ms": g["gpu_ms"],
+                                "gpu_iters": g["iters"], "gpu_keff": g["keff"],
+                                "sample": "Keff2D 00009.jpg, shipped input.txt keys (Convergence 1e-5), one thread"}
+    except Exception as e:  # a missing fixture must not cost the bench line
+        out["config0_00009"] = {"error": repr(e)}
+    try:
+        bits = np.load(os.path.join(gold, "schwarz163_bits.npy"))
+        vol = np.unpackbits(bits).reshape(128, 128, 128)
+        sweeps = 200
+        if refbind.have_ref():
+            t0 = time.perf_counter()
+            refbind.ref3d_solve(vol, tol=1e-30, max_iter=sweeps, threads=1, want_T=False)
+            tc = time.perf_counter() - t0
+            kind = "reference"
+        else:
+            t0 = time.perf_counter()
+            refbind.orc_gs3d_sweeps(vol, sweeps)
+            tc = time.perf_counter() - t0
+            kind = "port"
+        g = api.solve3d(vol, p, want_T=False)
+        g = api.solve3d(vol, p, want_T=False)
+        out["config2_schwarz163"] = {"kind": kind, "cores": 1, "cpu_seconds": tc, "cpu_sweeps": sweeps,
+                                     "cpu_mcell_updates_per_s": sweeps * vol.size / tc / 1e6,
+                                     "cpu_seconds_to_shipped_tol_extrapolated": tc / sweeps * 14600,
+                                     "gpu_ms": g["gpu_ms"], "gpu_iters": g["iters"], "gpu_keff": g["keff"],
+                                     "sample": f"Schwarz163 128^3: {sweeps} ParallelGS3D sweeps on one thread (the shipped tolerance "
+                                               "takes 14 600 sweeps: tests/golden/ref3d_schwarz163.json)"}
+    except Exception as e:
+        out["config2_schwarz163"] = {"error": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +326,48 @@ def main():
                      "gcell_updates_per_s": updates_per_step / (k_ms * 1e-3) / 1e9},
     }
 
+    # ---- e2e from PAGEABLE host memory (what a reference-style caller with a std::vector passes) -------------
+    pageable = np.array(harr, copy=True)
+    api.solve2d_batch(pageable, p)
+    dt_p, _ = timed(lambda: api.solve2d_batch(pageable, p))
+    out["e2e"]["pageable_value"] = world * n_img * args.steps / dt_p
+    out["e2e"]["pageable_note"] = "same call with the structures in ordinary (pageable) host memory"
+    del pageable
+
+    # ---- what bounds the batch kernel (SURVEY 8d, config-2 caveat): true DRAM fraction and issue-slot roofline ----
+    tr = out["roofline"]["traffic"]
+    if tr:
+        out["roofline"]["hbm_true"] = {"achieved": tr / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": tr / (k_ms * 1e-3) / 1e9 / peak,
+                                       "note": "measured DRAM bytes (ncu) / kernel time / measured HBM peak"}
+    try:
+        wi = float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_batch2d_mg"]["warp_inst_per_unit"])
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        issue_peak = sms * 4 * sm_hz                                   # 4 schedulers per SM, one warp instruction per clock each
+        issue = wi * n_img / (k_ms * 1e-3)
+        out["roofline"]["issue"] = {"bound": "issue", "achieved": issue / 1e12, "peak": issue_peak / 1e12,
+                                    "unit": "T warp-inst/s", "frac": issue / issue_peak,
+                                    "note": "warp instructions per image (ncu smsp__inst_executed.sum of the committed capture) "
+                                            "x images / kernel time, against SMs x 4 schedulers x SM clock under load"}
+    except Exception:
+        pass
+
+    # ---- configs[1] AS NAMED at N > 1: the same 10,000 images split across the GPUs (strong scaling) -----------
+    if world > 1:
+        i0, cnt = KD_image_shard(n_img, rank, world)
+        shard_dev = devm[i0:i0 + cnt].contiguous()
+        shard_host = host[i0:i0 + cnt].contiguous().pin_memory().numpy()
+        api.solve2d_batch(shard_dev, p)
+        dt_s, _ = timed(lambda: api.solve2d_batch(shard_dev, p))
+        api.solve2d_batch(shard_host, p)
+        dt_se, _ = timed(lambda: api.solve2d_batch(shard_host, p))
+        out["batch_split"] = {"workload": f"configs[1] as named: {n_img} images split over {world} GPUs ({cnt} on rank {rank}), "
+                              "no data-path collective", "scaling": "strong", "value": n_img * args.steps / dt_s,
+                              "e2e": n_img * args.steps / dt_se, "unit": UNIT, "ms_per_step": 1e3 * dt_s / args.steps,
+                              "e2e_ms_per_step": 1e3 * dt_se / args.steps}
+        del shard_dev
+
     if rank == 0 and not args.no_3d:
         n3 = 512
         vol = api.bernoulli_volume_dev((n3, n3, n3), 0.5, 1234, device=local)
@@ -289,32 +390,84 @@ def main():
                           "rel_residual": r3["rel_residual"], "status": r3["status"]}
         del vol
 
-    if world > 1 and not args.no_3d:
-        # configs[4]-shaped weak scaling of the z-slab solve: 1024 x 1024 x 128 planes per GPU (134 M cells per
-        # GPU, the same as the 512^3 single-GPU case; at 8 GPUs this IS configs[4], the 1024^3 volume)
-        from keff_cfd_b200 import dist as KD
+    if world == 1 and not args.no_3d and torch.cuda.get_device_properties(local).total_memory > 100e9:
+        # configs[4] on ONE GPU: the 1024^3 volume fits in 180 GB (about 60 GB of workspace)
         del devm
         torch.cuda.empty_cache()
+        n4 = 1024
+        vol = api.bernoulli_volume_dev((n4, n4, n4), 0.5, 1234, device=local)
+        api.solve3d(vol, p, want_T=False, device=local)
+        r4 = api.solve3d(vol, p, want_T=False, device=local)
+        out["solve3d_1024"] = {"workload": "configs[4] on one GPU: 1024^3 random binary volume, ks:kf 10:1",
+                               "gpu_ms": r4["gpu_ms"], "iters": r4["iters"], "ms_per_iter": r4["gpu_ms"] / max(r4["iters"], 1),
+                               "keff": r4["keff"], "rel_residual": r4["rel_residual"], "status": r4["status"]}
+        del vol
+        K.shutdown()                                                 # give the 60 GB back before the CPU legs
+        K.init(local)
+
+    if world > 1 and not args.no_3d:
+        from keff_cfd_b200 import dist as KD
+        try:
+            del devm
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
         KD.init_comm(rank, world, local)
-        nxs, nzg = 1024, 128 * world
-        z0, nzl = KD.slab_extent(nzg, rank, world)
-        loc = api.bernoulli_volume_dev((nzl, nxs, nxs), 0.5, 1234, z0=z0, device=local)
-        halo = KD.exchange_structure_halos(loc, rank, world)
-        del loc
         ps = api.default_params()
-        for _ in range(2):                                          # first call allocates the workspace
-            barrier()
-            r3 = KD.solve3d_slab(halo, z0, nzg, ps)
-        ms3 = max_over_ranks(float(r3["gpu_ms"]))
+
+        def slab_case(nxs, nzg, want_T=False):
+            z0, nzl = KD.slab_extent(nzg, rank, world)
+            loc = api.bernoulli_volume_dev((nzl, nxs, nxs), 0.5, 1234, z0=z0, device=local)
+            halo = KD.exchange_structure_halos(loc, rank, world)
+            del loc
+            for _ in range(2):                                      # first call allocates the workspace
+                barrier()
+                r = KD.solve3d_slab(halo, z0, nzg, ps, want_T=want_T)
+            r["gpu_ms"] = max_over_ranks(float(r["gpu_ms"]))
+            return r, z0, nzl
+
+        def slab_record(r, nxs, nzg, what):
+            return {"workload": what, "gpu_ms": r["gpu_ms"], "solves_per_s": 1e3 / r["gpu_ms"], "iters": r["iters"],
+                    "ms_per_iter": r["gpu_ms"] / max(r["iters"], 1), "keff": r["keff"], "rel_residual": r["rel_residual"],
+                    "status": r["status"], "gcell_iters_per_s": nxs * nxs * nzg * r["iters"] / (r["gpu_ms"] * 1e-3) / 1e9,
+                    "transport": "peer memory (NVLink stores from the solver's kernels)" if KD.peer_memory() else "NCCL"}
+
+        # (1) slab-vs-single parity on the record: a 256^3 splitmix volume in `world` slabs against rank 0 alone
+        npar = 256
+        rp, z0p, nzlp = slab_case(npar, npar, want_T=True)
+        parts = [torch.empty_like(rp["T"]) for _ in range(world)]
+        dist.all_gather(parts, rp["T"])
         if rank == 0:
-            out["slab3d"] = {"workload": f"1024x1024x{nzg} random binary volume in {world} z-slabs of 128 planes "
-                             "(configs[4] at 8 GPUs), ks:kf 10:1, halo planes + scalar all-reduces over NCCL",
-                             "gpu_ms": ms3, "solves_per_s": 1e3 / ms3, "iters": r3["iters"],
-                             "ms_per_iter": ms3 / max(r3["iters"], 1), "keff": r3["keff"],
-                             "rel_residual": r3["rel_residual"], "status": r3["status"],
-                             "gcell_iters_per_s": nxs * nxs * nzg * r3["iters"] / (ms3 * 1e-3) / 1e9,
-                             "scaling": "weak (compare gpu_ms with solve3d.gpu_ms of the 1-GPU line: 512^3, same cells per GPU)"}
-        del halo
+            full = api.bernoulli_volume_dev((npar, npar, npar), 0.5, 1234, device=local)
+            s1 = api.solve3d(full, ps, device=local)
+            Tfull = torch.cat(parts)
+            out["slab_parity"] = {"workload": f"256^3 random binary volume: {world} z-slabs vs the same solve on one GPU",
+                                  "keff_slab": rp["keff"], "keff_single": s1["keff"],
+                                  "keff_rel_diff": abs(rp["keff"] - s1["keff"]) / abs(s1["keff"]),
+                                  "T_maxdiff": float((Tfull - s1["T"]).abs().max().item()),
+                                  "iters_slab": rp["iters"], "iters_single": s1["iters"], "status": rp["status"]}
+            del full, s1, Tfull
+        del parts, rp
+        torch.cuda.empty_cache()
+        barrier()
+        # (2) weak scaling: 1024 x 1024 x 128 planes per GPU (134 M cells per GPU = the 512^3 single-GPU case)
+        nxs = 1024
+        rw, _, _ = slab_case(nxs, 128 * world)
+        if rank == 0:
+            out["slab3d"] = slab_record(rw, nxs, 128 * world, f"1024x1024x{128 * world} random binary volume in {world} z-slabs of "
+                                        "128 planes (configs[4] at 8 GPUs), ks:kf 10:1")
+            out["slab3d"]["scaling"] = "weak (compare gpu_ms with solve3d.gpu_ms of the same line: 512^3, same cells per GPU)"
+            if "solve3d" in out:
+                out["slab3d"]["weak_efficiency"] = out["solve3d"]["gpu_ms"] / rw["gpu_ms"]
+        # (3) configs[4] AS NAMED: the 1024^3 volume in `world` slabs (strong scaling)
+        if world != 8:
+            rs, _, _ = slab_case(nxs, nxs)
+        else:
+            rs = rw
+        if rank == 0:
+            out["slab3d_strong"] = slab_record(rs, nxs, nxs, f"configs[4] as named: 1024^3 random binary volume in {world} z-slabs "
+                                               f"of {nxs // world} planes, ks:kf 10:1")
+            out["slab3d_strong"]["scaling"] = "strong (1-GPU time of the same volume: solve3d_1024 of the N = 1 line)"
 
     if rank == 0 and not args.no_cpu:
         from oracle import refbind
@@ -337,6 +490,8 @@ def main():
                                            "1e-3..1e-2 away from the discrete solution on these images (SURVEY 8c); the GPU "
                                            "results are at TRUE relative residual 1e-8.  Parity proper is tests/test_gpu_parity.py "
                                            "(tight reference, Keff within 1e-5)"}
+        if world == 1:
+            out["cpu_baseline_others"] = cpu_other_configs(refbind, api, p)
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if rank == 0:

@@ -5,7 +5,13 @@
  * Conventions: plain pointers and sizes only; the caller owns every host buffer; the library owns
  * all device memory, streams and communicator state; no exit(), no stdin, no stdout; every function
  * returns 0 on success or a negative KEFFB200_E* code, with text from keffb200_last_error().
- * One context per process (one process per GPU); calls are not re-entrant.
+ * One context per GPU: a process binds one GPU (keffb200_init -- the one-process-per-GPU layout) or
+ * several (keffb200_init_multi); calls are made from one host thread and are not re-entrant.
+ *
+ * Streams: every kernel runs on the library's own non-blocking stream.  Host-buffer entry points are
+ * synchronous.  Device-buffer entry points (*_dev) read their inputs on that stream: if another stream is
+ * still writing them, call keffb200_wait_stream(that stream) first; they return after their outputs are
+ * complete (the library stream is synchronised before the call returns).
  *
  * Structure semantics are fixed at this boundary: `solid` is one byte per cell, 1 = solid (ks),
  * anything else = fluid (kf); layout [z][y][x], x fastest -- the reference's
@@ -38,10 +44,14 @@ extern "C" {
 typedef struct keffb200_params {
   double ks, kf;          /* TCsolid, TCfluid */
   double tl, tr;          /* TempLeft, TempRight */
-  double convergence;     /* ConvergeCriteria: max relative change of Keff between two checks */
+  double convergence;     /* ConvergeCriteria.  The reference stops when Keff changes by less than this between two
+                             checks 100 sweeps apart (Keff2D/keff2D.h:825-847), 5-7e-4 away from the discrete solution
+                             at the shipped 1e-5.  Here the key sets the two targets below when they are left at 0:
+                             the shipped value gives the defaults, a tighter value tightens both, a looser one never
+                             loosens them (the field is frozen once the targets are met, so Keff no longer changes). */
   long max_iter;          /* MAX_ITER: cap on solver iterations */
-  double rel_residual;    /* stop when ||b - A T||2 / ||b||2 <= this (default 1e-8) */
-  double flux_balance;    /* ... and |QL - QR| / |Keff| <= this (default 1e-6) */
+  double rel_residual;    /* stop when ||b - A T||2 / ||b||2 <= this; 0 (default) = min(1e-8, 1e-3 * convergence) */
+  double flux_balance;    /* ... and |QL - QR| / |Keff| <= this; 0 (default) = min(1e-6, 0.1 * convergence) */
   int check_every;        /* iterations between host-visible convergence checks (default 32) */
   int flags;              /* KEFFB200_F_* */
 } keffb200_params;
@@ -74,6 +84,15 @@ typedef struct keffb200_result {
 /* Bind the process to CUDA device `device` (replaces initializeGPU's cudaSetDevice(0),
  * Keff2DGPU/keff2D.cuh:606-683; memory is allocated lazily by the solves and cached). */
 int keffb200_init(int device);
+/* Bind the process to GPUs 0..n_gpus-1 (n_gpus <= 0: every visible GPU), one context and one host thread per GPU
+ * inside the library.  The host-buffer calls then fan out by themselves: keffb200_solve2d_batch gives every GPU a
+ * contiguous share of the images (the reference's OpenMP loop over images, Keff2D/keff2D.cpp:341, with GPUs in the
+ * place of threads; no communication), keffb200_solve3d cuts a large volume into z-slabs whose halo planes and
+ * reductions travel as NVLink stores between the GPUs' memories (volumes below keffb200_set_slab_min_cells stay on
+ * GPU 0).  The *_dev entry points and keffb200_solve2d use GPU 0. */
+int keffb200_init_multi(int n_gpus);
+int keffb200_device_count(void);               /* GPUs bound by init / init_multi */
+void keffb200_set_slab_min_cells(long cells);  /* default 2^26; < 0 restores it */
 void keffb200_shutdown(void); /* replaces unInitializeGPU, Keff2DGPU/keff2D.cuh:685-723 */
 const char* keffb200_last_error(void);
 const char* keffb200_version(void);
@@ -110,7 +129,12 @@ int keffb200_solve2d_batch_dev(const uint8_t* d_solid, int n_img, int nx, int ny
 /* Size of the opaque communicator id that rank 0 creates and the host broadcasts to all ranks. */
 #define KEFFB200_COMM_ID_BYTES 128
 int keffb200_comm_id(void* id128);                       /* rank 0: ncclGetUniqueId */
-int keffb200_dist_init(int rank, int world, const void* id128); /* all ranks: ncclCommInitRank */
+/* All ranks: ncclCommInitRank, then every rank maps every other rank's mailbox through CUDA IPC.  When that
+ * succeeds on all ranks the slab solve's halo planes and reductions travel as NVLink stores issued by the
+ * solver's own kernels and NCCL is off the data path (keffb200_dist_peer_memory() == 1); otherwise, or with
+ * KEFFB200_SLAB_NCCL set, they go through ncclSend/ncclRecv/ncclAllReduce. */
+int keffb200_dist_init(int rank, int world, const void* id128);
+int keffb200_dist_peer_memory(void);
 void keffb200_dist_shutdown(void);
 /* Solve a global nx*ny*nz_global volume whose planes [z0, z0+nz_local) live on this rank.
  * d_solid_halo: (nz_local+2) planes, plane 0 / plane nz_local+1 = the neighbouring ranks' boundary
@@ -147,6 +171,9 @@ int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, con
  * calls made in between, host-buffer copies included.  stop() waits for its event. */
 int keffb200_timer_start(void);
 int keffb200_timer_stop(float* ms);
+/* Make the library's stream wait for the work queued so far on `stream` (a cudaStream_t; NULL = the legacy
+ * default stream).  See "Streams" at the top. */
+int keffb200_wait_stream(void* stream);
 
 /* Synthetic input generator for benchmarks and tests (no reference counterpart): voxel i of the
  * range [first_index, first_index + n) is solid iff splitmix64(seed ^ i) < p * 2^64.  The same rule

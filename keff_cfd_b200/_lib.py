@@ -41,7 +41,8 @@ EXPORTS = [
     "keffb200_solve3d", "keffb200_solve3d_dev", "keffb200_solve2d_batch_dev", "keffb200_comm_id",
     "keffb200_dist_init", "keffb200_dist_shutdown", "keffb200_solve3d_slab_dev", "keffb200_apply",
     "keffb200_flux", "keffb200_bench_apply_dev", "keffb200_gen_bernoulli_dev", "keffb200_precond",
-    "keffb200_timer_start", "keffb200_timer_stop",
+    "keffb200_timer_start", "keffb200_timer_stop", "keffb200_init_multi", "keffb200_device_count",
+    "keffb200_set_slab_min_cells", "keffb200_dist_peer_memory", "keffb200_wait_stream",
 ]
 
 _lib = None
@@ -66,6 +67,10 @@ def lib():
         L.keffb200_version.restype = C.c_char_p
         L.keffb200_launch_count.restype = C.c_long
         L.keffb200_init.argtypes = [C.c_int]
+        L.keffb200_init_multi.argtypes = [C.c_int]
+        L.keffb200_set_slab_min_cells.argtypes = [C.c_long]
+        L.keffb200_set_slab_min_cells.restype = None
+        L.keffb200_wait_stream.argtypes = [C.c_void_p]
         L.keffb200_default_params.argtypes = [PP]
         L.keffb200_solve2d.argtypes = [u8p, C.c_int, C.c_int, PP, dp, dp, dp, dp, RP]
         L.keffb200_solve2d_batch.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, RP]
@@ -102,6 +107,26 @@ def init(device=0):
         _inited = device
 
 
+def init_multi(n_gpus=0):
+    """Bind this process to GPUs 0..n-1 (0 = all visible): host-buffer batch and volume solves fan out over them."""
+    global _inited
+    check(lib().keffb200_init_multi(int(n_gpus)))
+    _inited = 0
+    return lib().keffb200_device_count()
+
+
+def order_after_torch(tensor=None):
+    """Device-buffer calls read their inputs on the library's own stream: make it wait for what torch has queued
+    on its current stream (the kernels still writing those tensors)."""
+    try:
+        import torch
+    except ImportError:
+        return
+    if torch.cuda.is_available() and _inited is not None:
+        dev = tensor.device if tensor is not None and getattr(tensor, "is_cuda", False) else torch.device("cuda", _inited)
+        check(lib().keffb200_wait_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
+
 def ensure(device=None, tensor=None):
     """One process is bound to ONE GPU.  device=None keeps the binding made by init() (binding to GPU 0 if there
     is none yet); an explicit device re-binds only if it differs.  A CUDA tensor argument must live on the bound
@@ -120,3 +145,8 @@ def shutdown():
     if _lib is not None:
         _lib.keffb200_shutdown()
     _inited = None
+    try:
+        from . import dist
+        dist._comm_ready = False
+    except Exception:
+        pass

@@ -131,6 +131,7 @@ def solve3d(solid, params=None, T_init=None, want_T=True, want_q=False, device=N
     if _is_cuda(solid):
         import torch
         T = torch.empty((nz, ny, nx), dtype=torch.float64, device=solid.device) if want_T else None
+        _lib.order_after_torch(solid)
         check(lib().keffb200_solve3d_dev(_addr(solid), nx, ny, nz, C.byref(p), _addr(T_init), _addr(T), C.byref(r)))
         return _res(r, T=T)
     solid = np.ascontiguousarray(solid, dtype=np.uint8) if isinstance(solid, np.ndarray) else solid
@@ -165,6 +166,7 @@ def solve2d_batch(solid, params=None, want_T=False, device=None):
     if _is_cuda(solid):
         import torch
         T = torch.empty((n, ny, nx), dtype=torch.float64, device=solid.device) if want_T else None
+        _lib.order_after_torch(solid)
         check(lib().keffb200_solve2d_batch_dev(_addr(solid), n, nx, ny, C.byref(p), _addr(T), res))
     else:
         solid = np.ascontiguousarray(solid, dtype=np.uint8) if isinstance(solid, np.ndarray) else solid
@@ -230,6 +232,7 @@ def bench_apply(solid_dev, params=None, reps=20, device=None):
     p = params or default_params()
     nz, ny, nx = solid_dev.shape
     ms = C.c_float()
+    _lib.order_after_torch(solid_dev)
     check(lib().keffb200_bench_apply_dev(_addr(solid_dev), nx, ny, nz, C.byref(p), reps, C.byref(ms)))
     return ms.value
 

@@ -218,11 +218,10 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
     }
     F.dx = (float)C.diff[0];
     F.dy = (float)C.diff[1];
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c.attr_batch) {  // function attributes are per device: the flag lives in the context
       KB_CUDA(cudaFuncSetAttribute(k_batch2d_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
       KB_CUDA(cudaFuncSetAttribute(k_batch2d_mg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM));
-      attr_set = true;
+      c.attr_batch = true;
     }
     if (mgk) {
       static const float om = getenv("KEFFB200_BATCH_OMEGA") ? (float)atof(getenv("KEFFB200_BATCH_OMEGA")) : 0.8f;

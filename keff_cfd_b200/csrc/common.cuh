@@ -35,13 +35,85 @@ struct Scal {
   double rz[2];   // r.z, double-buffered by iteration parity
   double pq;      // p.Ap of the current iteration
   double rr, bb;  // ||r||^2, ||b||^2
-  double tmp[4];  // finalize outputs before the (optional) all-reduce
+  double tmp[4];  // reduction outputs before an NCCL all-reduce (peer-memory all-reduces never leave the kernel)
   double ql, qr;  // boundary flux sums
   double thr2;    // squared relative-residual threshold
   long long it;   // iterations completed
   int done;       // sticky convergence flag
-  int pad;
+  int fault;      // a peer-memory wait timed out (a neighbour never delivered): the solve is void
 };
+
+// ---- peer memory (z-slabs over NVLink): mailboxes, flags, system-scope accesses -------------------
+// Every rank owns one Mail block in its own HBM; every other rank of the slab group has it mapped
+// (cudaDeviceEnablePeerAccess inside one process, CUDA IPC between processes) and writes into it
+// with ordinary stores.  Nothing is ever read remotely.
+constexpr int KB_MAX_RANKS = 16;
+constexpr int KB_HALO_FIELDS = 160;  // p, x, u, two iterates, 6 arrays per stored level
+struct MailSlot {
+  double v[4];
+  unsigned long long seq;
+  unsigned long long pad[3];
+};
+// windows: the buffers of a rank that its peers store into
+enum { W_X = 0, W_P, W_U, W_XF0, W_XF1, W_POOL, W_COUNT };
+struct WinTable {                        // what a rank publishes about its workspace before a slab solve
+  unsigned long long base[W_COUNT];      // device addresses in the owner's address space
+  unsigned char handle[W_COUNT][64];     // the same allocations as CUDA IPC handles (other processes map these)
+  unsigned long long gen[W_COUNT];       // bumped whenever the owner re-allocates the window: peers re-map
+  long long pid;                         // owner process: peers inside it use `base` directly
+  int nz, z0;                            // the owner's slab: plane count, first global plane
+};
+struct Mail {
+  MailSlot ar[2][KB_MAX_RANKS];          // all-reduce contributions: [sequence parity][source rank]
+  unsigned int halo[KB_HALO_FIELDS][2];  // cumulative arrival counters: [field][0 = my lower halo, 1 = my upper halo]
+  unsigned int gath[KB_MAX_RANKS];       // cumulative arrival counters of all-gathers: [source rank]
+  unsigned long long bar[KB_MAX_RANKS];  // barrier: [source rank] = barrier sequence number
+  WinTable win[KB_MAX_RANKS];            // [source rank]
+};
+// halo counter ids
+enum { HF_X = 0, HF_P, HF_U, HF_XF0, HF_XF1, HF_LEVEL0 = 8 };  // + 6 * level + {u, t0, t1, e, cz, dinv}
+enum { HL_U = 0, HL_T0, HL_T1, HL_E, HL_CZ, HL_DINV };
+// what a reduction kernel needs to finish its sum across the ranks (world <= 1: nothing to do)
+struct ArLink {
+  int world, rank;
+  unsigned long long* seq;   // my count of all-reduces so far (device memory; identical on every rank)
+  Mail* mail[KB_MAX_RANKS];  // every rank's mailbox as mapped here (mail[rank] is my own)
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr unsigned long long KB_WAIT_NS = 4000000000ull;  // a peer that stays silent this long is gone
+
+// Wait until a cumulative arrival counter has reached `expect`; false on timeout.  Counters wrap
+// (32 bit), so the comparison is on the signed difference.
+__device__ __forceinline__ bool wait_counter(const unsigned int* flag, unsigned int expect) {
+  if ((int)(ld_acquire_sys(flag) - expect) >= 0) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  while ((int)(ld_acquire_sys(flag) - expect) < 0) {
+    __nanosleep(64);
+    if (globaltimer_ns() - t0 > KB_WAIT_NS) return false;
+  }
+  return true;
+}
 
 struct Faces {
   double w, e, n, s, f, b, diag;

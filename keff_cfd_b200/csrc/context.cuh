@@ -1,4 +1,6 @@
-// context.cuh -- process-wide state of libkeffb200 (one process per GPU).
+// context.cuh -- per-GPU state of libkeffb200.  One context per GPU: a process bound to one GPU (the
+// torchrun layout, keffb200_init) has one; a process that drives several (keffb200_init_multi) has one per
+// device, each used by one host thread at a time -- the thread's current context is a thread-local pointer.
 #pragma once
 #include <dlfcn.h>
 #include <stdarg.h>
@@ -40,6 +42,35 @@ struct Nccl {
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
+// Peer-memory link of a z-slab group (one per context).  Built once (keffb200_init_multi inside one process,
+// keffb200_dist_init between processes: the mailboxes are mapped into every rank), refreshed before every
+// slab solve (the workspace windows of the neighbours, published through the mailboxes).
+struct Link {
+  bool p2p = false;  // mailboxes mapped: halo planes and all-reduces travel as NVLink stores, NCCL is not on the path
+  bool ipc = false;  // the peers are other processes: windows are CUDA IPC mappings
+  int rank = 0, world = 1;
+  Mail* mail[KB_MAX_RANKS] = {};         // every rank's mailbox as mapped here (mail[rank] = my own allocation)
+  unsigned long long* ar_seq = nullptr;  // device: all-reduces done (reset with the mailbox before a solve)
+  unsigned long long bar_seq = 0;        // host: barriers done
+  unsigned int expect[KB_HALO_FIELDS][2] = {};  // host: arrival counts my halos must have reached before their next use
+  unsigned int expect_g = 0;                    // the same for all-gathers (per source rank; every source sends the same)
+  // neighbours' windows as mapped here: [0] = rank-1, [1] = rank+1; pool[r] = every rank's level pool
+  char* nb[2][W_COUNT] = {};
+  int nb_nz[2] = {0, 0};
+  char* pool[KB_MAX_RANKS] = {};
+  // CUDA IPC mappings kept open between solves (re-opened when a peer re-allocates)
+  struct IpcMap {
+    unsigned char handle[64];
+    unsigned long long gen = 0;
+    void* ptr = nullptr;
+  } ipcw[KB_MAX_RANKS][W_COUNT], ipc_mail[KB_MAX_RANKS];
+  unsigned long long win_gen[W_COUNT] = {};  // my windows' allocation generations
+  // Windows other processes have mapped must not be freed under them (CUDA IPC: undefined behaviour): a window that
+  // has to grow is retired instead and freed at shutdown, after every rank has closed its mappings.
+  std::vector<void*> retired;
+  WinTable* h_win = nullptr;  // pinned staging of window tables
+};
+
 struct Ctx {
   bool ready = false;
   int device = -1, sms = 0;
@@ -75,12 +106,28 @@ struct Ctx {
   size_t cap_stageT = 0;
   double* stageT = nullptr;
   Nccl nccl;
+  Link link;
   bool dist_active = false;  // true only inside a slab solve: halo exchange + all-reduces enabled
+  // scalar records of the last two convergence checks (pinned): the host reads check k while check k+1 is queued
+  Scal* hring = nullptr;
+  cudaEvent_t evb[2] = {nullptr, nullptr};
+  // per-device function attributes already applied (dynamic shared memory sizes)
+  bool attr_batch = false, attr_ws = false;
 };
 
+constexpr int KB_MAX_GPUS = 16;
+inline Ctx* ctx_table() {
+  static Ctx t[KB_MAX_GPUS];
+  return t;
+}
+inline Ctx*& ctx_current() {
+  static thread_local Ctx* cur = nullptr;
+  return cur;
+}
+// the calling thread's context (context 0 unless a fan-out worker bound another one)
 inline Ctx& ctx() {
-  static Ctx c;
-  return c;
+  Ctx* c = ctx_current();
+  return c ? *c : ctx_table()[0];
 }
 
 inline int fail(int code, const char* fmt, ...) {

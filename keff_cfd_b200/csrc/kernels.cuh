@@ -638,61 +638,142 @@ __global__ void __launch_bounds__(256) k_cg_dir(double* __restrict__ p, const do
 }
 
 // ------------------------------------------------------------------------------------------------
-// single-block finalizers: deterministic sums of per-CTA partials + the scalar recurrences
+// One-block reduction + all-reduce + scalar step.  Every dot product of the iteration ends here: the
+// per-CTA partials of the producing kernel are summed in a fixed order (bit-reproducible), the sum is
+// completed across the slab ranks THROUGH PEER MEMORY -- every rank stores its contribution into every
+// other rank's mailbox (NVLink stores), waits for the others' to land in its own, and adds them in rank
+// order, so all ranks hold bit-identical scalars and take identical branches -- and the scalar
+// recurrence of the step (iteration count, stop flag) is applied, all in one launch.
+//   phase 0: everything (single GPU, or peer memory)
+//   phase 1: the local sum only, into S->tmp (an NCCL all-reduce of S->tmp follows on the stream)
+//   phase 2: the scalar step from S->tmp
 // ------------------------------------------------------------------------------------------------
-// what: 0 -> p.q (stride 3, slot 0) into S->pq
-//       1 -> {r.z, r.r} (stride 2) into S->tmp[0..1]
-//       2 -> INIT {r.z, r.r, b.b} (stride 3) into S->tmp[0..2]
-//       3 -> RESID {-, r.r, |r|1} (stride 3) into S->tmp[1..2]
-//       4 -> flux {QL, QR} (stride 2) into S->tmp[0..1]
-//       5 -> r.z of the multigrid post pass (stride 3, slot 0) into S->tmp[0]
-__global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int n, int what, Scal* S) {
-  __shared__ double red[32 * 3];
-  if (S->done && (what <= 1 || what == 5)) return;
-  const int stride = (what == 1 || what == 4) ? 2 : 3;
-  double acc[3] = {0, 0, 0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    acc[0] += partials[i * stride];
-    acc[1] += partials[i * stride + 1];
-    if (stride == 3) acc[2] += partials[i * stride + 2];
+enum { RS_PQ = 0, RS_RR_MG = 1, RS_RZ_MG = 2, RS_INIT = 3, RS_ITER = 4, RS_RESID = 5, RS_FLUX = 6 };
+// what          partials (stride: slots)      step
+// RS_PQ         3: 0                          S->pq
+// RS_RR_MG      2: 1                          S->rr, ++S->it, stop flag              (multigrid path)
+// RS_RZ_MG      3: 0                          S->rz[arg]
+// RS_INIT       3: 0,1,2 = r.z, r.r, b.b      S->rz[0], S->rr, S->bb, it = 0, stop flag
+// RS_ITER       2: 0,1   = r.z, r.r           S->rz[arg ^ 1], S->rr, ++S->it, stop flag   (diagonal path)
+// RS_RESID      3: 1,2   = r.r, sum|r|        S->tmp[1], S->tmp[2]
+// RS_FLUX       2: 0,1   = QL, QR             S->ql, S->qr        (runs once the stop flag is up, or arg = 1)
+
+// complete v[0..3] (valid in thread 0 on entry, in every thread on return) over the ranks of the link
+__device__ __forceinline__ void ar_sum(double (&v)[4], const ArLink& ar, Scal* S) {
+  __shared__ unsigned long long s_seq;
+  __shared__ double s_in[KB_MAX_RANKS][4];
+  __shared__ double s_out[4];
+  const int t = threadIdx.x;
+  if (t == 0) {
+    s_seq = ++(*ar.seq);
+#pragma unroll
+    for (int k = 0; k < 4; k++) s_out[k] = v[k];
   }
-  block_sum<3>(acc, red);
-  if (threadIdx.x == 0) {
-    if (what == 0) S->pq = acc[0];
-    else if (what == 5) S->tmp[0] = acc[0];
-    else if (what == 3) { S->tmp[1] = acc[1]; S->tmp[2] = acc[2]; }
-    else { S->tmp[0] = acc[0]; S->tmp[1] = acc[1]; S->tmp[2] = acc[2]; }
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  if (t < ar.world) {
+    MailSlot* dst = &ar.mail[t]->ar[seq & 1][ar.rank];
+#pragma unroll
+    for (int k = 0; k < 4; k++) reinterpret_cast<volatile double*>(dst->v)[k] = s_out[k];
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+    const MailSlot* src = &ar.mail[ar.rank]->ar[seq & 1][t];
+    const unsigned long long t0 = globaltimer_ns();
+    bool ok = true;
+    while (ld_acquire_sys(&src->seq) != seq) {
+      if (globaltimer_ns() - t0 > KB_WAIT_NS) {
+        ok = false;
+        break;
+      }
+    }
+    if (!ok) S->fault = 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s_in[t][k] = ok ? reinterpret_cast<const volatile double*>(src->v)[k] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    double a = 0.0;
+    for (int r = 0; r < ar.world; r++) a += s_in[r][k];
+    v[k] = a;
   }
 }
 
-// scalar steps (run after the optional all-reduce of S->tmp)
-__global__ void k_step_init(Scal* S) {
-  S->rz[0] = S->tmp[0];
-  S->rr = S->tmp[1];
-  S->bb = S->tmp[2];
-  S->it = 0;
-  S->done = !(S->tmp[1] > S->thr2 * S->tmp[2]);
-}
-__global__ void k_step_iter(Scal* S, int par) {
-  if (S->done) return;
-  S->rz[par ^ 1] = S->tmp[0];
-  S->rr = S->tmp[1];
-  S->it += 1;
-  if (!(S->tmp[1] > S->thr2 * S->bb)) S->done = 1;
-}
-__global__ void k_step_flux(Scal* S) {
-  S->ql = S->tmp[0];
-  S->qr = S->tmp[1];
+template <int WHAT>
+__global__ void __launch_bounds__(512) k_reduce_step(const double* __restrict__ partials, int n, Scal* S, int arg, int phase,
+                                                     const ArLink ar) {
+  __shared__ double red[32 * 3];
+  const bool iter_step = WHAT == RS_PQ || WHAT == RS_RR_MG || WHAT == RS_RZ_MG || WHAT == RS_ITER;
+  if (iter_step && S->done) return;
+  if (WHAT == RS_FLUX && !S->done && !arg) return;
+  constexpr int stride = (WHAT == RS_RR_MG || WHAT == RS_ITER || WHAT == RS_FLUX) ? 2 : 3;
+  constexpr int s0 = (WHAT == RS_RR_MG || WHAT == RS_RESID) ? 1 : 0;                     // first slot used
+  constexpr int nv = WHAT == RS_INIT ? 3 : (WHAT == RS_ITER || WHAT == RS_RESID || WHAT == RS_FLUX) ? 2 : 1;
+  double v[4] = {0, 0, 0, 0};
+  if (phase != 2) {
+    double acc[3] = {0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < nv; k++) acc[k] += partials[i * stride + s0 + k];
+    }
+    block_sum<3>(acc, red);
+#pragma unroll
+    for (int k = 0; k < 3; k++) v[k] = acc[k];
+    if (phase == 1) {
+      if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < nv; k++) S->tmp[k] = v[k];
+      return;
+    }
+    if (ar.world > 1) ar_sum(v, ar, S);
+  } else {
+#pragma unroll
+    for (int k = 0; k < nv; k++) v[k] = S->tmp[k];
+  }
+  if (threadIdx.x != 0) return;
+  if (WHAT == RS_PQ) S->pq = v[0];
+  if (WHAT == RS_RZ_MG) S->rz[arg] = v[0];
+  if (WHAT == RS_RR_MG) {
+    S->rr = v[0];
+    S->it += 1;
+    if (!(v[0] > S->thr2 * S->bb)) S->done = 1;
+  }
+  if (WHAT == RS_INIT) {
+    S->rz[0] = v[0];
+    S->rr = v[1];
+    S->bb = v[2];
+    S->it = 0;
+    S->done = !(v[1] > S->thr2 * v[2]);
+  }
+  if (WHAT == RS_ITER) {
+    S->rz[arg ^ 1] = v[0];
+    S->rr = v[1];
+    S->it += 1;
+    if (!(v[1] > S->thr2 * S->bb)) S->done = 1;
+  }
+  if (WHAT == RS_RESID) {
+    S->tmp[1] = v[0];
+    S->tmp[2] = v[1];
+  }
+  if (WHAT == RS_FLUX) {
+    S->ql = v[0];
+    S->qr = v[1];
+  }
+  if (S->fault) S->done = 1;  // a rank went silent: let every queued kernel drain, the host reports it
 }
 
 // ------------------------------------------------------------------------------------------------
 // boundary-flux integration: QL = sum c_wall (T(x=0) - TL), QR = sum c_wall (TR - T(x=nx-1))
 // (Keff2D/keff2D.cpp:151-170, Keff3D/keff3D.cpp:145-163).  One thread per (z,y) row.
 // ------------------------------------------------------------------------------------------------
+// S != nullptr: in-loop use -- the sums are only needed once the stop flag is up (the flux balance is part of the
+// stop rule), so the kernel returns at once while the iteration is still running.
 __global__ void __launch_bounds__(256) k_flux(const double* __restrict__ T, const uint8_t* __restrict__ code,
                                               const Coef C, const Dom D, double* __restrict__ qL,
-                                              double* __restrict__ qR, double* __restrict__ partials) {
+                                              double* __restrict__ qR, double* __restrict__ partials,
+                                              const Scal* __restrict__ S) {
   __shared__ double red[32 * 2];
+  if (S && !S->done) return;
   const long rows = (long)D.ny * D.nz;
   double acc[2] = {0, 0};
   for (long row = blockIdx.x * (long)blockDim.x + threadIdx.x; row < rows; row += (long)gridDim.x * blockDim.x) {

@@ -680,16 +680,4 @@ __global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, doubl
   }
 }
 
-// scalar steps of the multigrid-preconditioned iteration
-__global__ void k_step_mg_rr(Scal* S) {
-  if (S->done) return;
-  S->rr = S->tmp[1];
-  S->it += 1;
-  if (!(S->tmp[1] > S->thr2 * S->bb)) S->done = 1;
-}
-__global__ void k_step_mg_rz(Scal* S, int slot) {
-  if (S->done) return;
-  S->rz[slot] = S->tmp[0];
-}
-
 }  // namespace kb

@@ -8,6 +8,9 @@
 #include "context.cuh"
 #include "kernels.cuh"
 #include "mg.cuh"
+#include "peer.cuh"
+
+#include <thread>
 
 namespace kb {
 
@@ -20,11 +23,15 @@ int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int 
 static keffb200_params norm_params(const keffb200_params* p) {
   keffb200_params P;
   if (p) P = *p; else keffb200_default_params(&P);
-  if (!(P.rel_residual > 0)) P.rel_residual = 1e-8;
-  if (!(P.flux_balance > 0)) P.flux_balance = 1e-6;
   if (P.check_every <= 0) P.check_every = 32;
   if (P.max_iter <= 0) P.max_iter = 500000;
   if (!(P.convergence > 0)) P.convergence = 1e-5;
+  // The reference's only stop control is `Convergence` (relative change of Keff between two checks,
+  // Keff2D/keff2D.h:825-847).  Here a check happens once the residual target is met and the field is frozen from
+  // then on, so the key acts through the two targets it implies: at the shipped 1e-5 they are the defaults
+  // (1e-8, 1e-6); a tighter Convergence tightens both in proportion, a looser one never loosens them.
+  if (!(P.rel_residual > 0)) P.rel_residual = std::max(1e-13, std::min(1e-8, 1e-3 * P.convergence));
+  if (!(P.flux_balance > 0)) P.flux_balance = std::max(1e-11, std::min(1e-6, 1e-1 * P.convergence));
   return P;
 }
 
@@ -55,7 +62,10 @@ static int ensure_ws(const Dom& D) {
   Ctx& c = ctx();
   const size_t plane = (size_t)D.nx * D.ny, need = plane * (D.nz + 2);
   if (need > c.cap_field) {
-    for (double** f : {&c.x, &c.r, &c.p, &c.q}) {
+    link_release_window(c, W_X, c.x);
+    link_release_window(c, W_P, c.p);
+    c.x = c.p = nullptr;
+    for (double** f : {&c.r, &c.q}) {
       if (*f) cudaFree(*f);
       *f = nullptr;
     }
@@ -77,7 +87,7 @@ static int ensure_ws(const Dom& D) {
   }
   const size_t need_u = (size_t)mg_pitch(D.nx) * D.ny * (D.nz + 2);
   if (need_u > c.cap_u) {
-    if (c.u) cudaFree(c.u);
+    link_release_window(c, W_U, c.u);
     c.u = nullptr;
     c.cap_u = 0;
     KB_CUDA(cudaMalloc(&c.u, need_u * sizeof(float)));
@@ -105,15 +115,52 @@ static int nccl_check(int rc, const char* what) {
 
 static int allreduce_tmp(double* dptr, int count) {
   Nccl& n = ctx().nccl;
-  if (n.world <= 1 || !n.comm || !ctx().dist_active) return 0;
+  if (n.world <= 1 || !n.comm || !ctx().dist_active || ctx().link.p2p) return 0;
   return nccl_check(n.AllReduce(dptr, dptr, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, n.comm, ctx().st), "ncclAllReduce");
 }
 
-// exchange the boundary planes of a halo'ed field with the z neighbours (f points at the halo plane)
+static ArLink ar_link() {
+  Ctx& c = ctx();
+  ArLink a;
+  memset(&a, 0, sizeof a);
+  a.world = 1;
+  if (c.dist_active && c.link.p2p) {
+    a.world = c.link.world;
+    a.rank = c.link.rank;
+    a.seq = c.link.ar_seq;
+    for (int r = 0; r < c.link.world; r++) a.mail[r] = c.link.mail[r];
+  }
+  return a;
+}
+
+// sum of the per-CTA partials of the kernel just launched + all-reduce over the slab ranks + scalar step:
+// one launch (single GPU, peer memory), or sum / ncclAllReduce / step when the ranks only share NCCL
+template <int WHAT>
+static int reduce_step(int n, int arg) {
+  Ctx& c = ctx();
+  constexpr int nv = WHAT == RS_INIT ? 3 : (WHAT == RS_ITER || WHAT == RS_RESID || WHAT == RS_FLUX) ? 2 : 1;
+  const bool via_nccl = c.dist_active && c.nccl.world > 1 && c.nccl.comm && !c.link.p2p;
+  k_reduce_step<WHAT><<<1, 512, 0, c.st>>>(c.partials, n, c.S, arg, via_nccl ? 1 : 0, ar_link());
+  KB_LAUNCHED();
+  if (via_nccl) {
+    KB_TRY(allreduce_tmp(c.S->tmp, nv));
+    k_reduce_step<WHAT><<<1, 512, 0, c.st>>>(c.partials, n, c.S, arg, 2, ar_link());
+    KB_LAUNCHED();
+  }
+  return 0;
+}
+
+// exchange the boundary planes of a halo'ed FP64 field (x or p) with the z neighbours (f points at the halo plane)
 static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
-  Nccl& n = ctx().nccl;
-  if (n.world <= 1 || !n.comm || !ctx().dist_active) return 0;
+  Ctx& c = ctx();
+  Nccl& n = c.nccl;
+  if (!c.dist_active) return 0;
   const size_t plane = (size_t)D.nx * D.ny;
+  if (c.link.p2p) {
+    const bool is_x = f_halo == c.x;
+    return link_exchange(c, is_x ? HF_X : HF_P, is_x ? W_X : W_P, (char*)(f_halo + plane), plane * 8, D.nz);
+  }
+  if (n.world <= 1 || !n.comm) return 0;
   double* lo_halo = f_halo;
   double* first = f_halo + plane;
   double* last = f_halo + plane * D.nz;
@@ -131,10 +178,14 @@ static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
   return 0;
 }
 
-// same for any plane-major array: plane0 = local plane 0, halo planes at -1 and nz
-static int exchange_planes(void* plane0, size_t plane_bytes, int nz, cudaStream_t st) {
-  Nccl& n = ctx().nccl;
-  if (n.world <= 1 || !n.comm || !ctx().dist_active) return 0;
+// same for any plane-major array inside window `win` of the workspace: plane0 = local plane 0, halo planes at
+// -1 and nz; `field` names its arrival counters
+static int exchange_planes(int field, int win, void* plane0, size_t plane_bytes, int nz, cudaStream_t st) {
+  Ctx& c = ctx();
+  Nccl& n = c.nccl;
+  if (!c.dist_active) return 0;
+  if (c.link.p2p) return link_exchange(c, field, win, (char*)plane0, plane_bytes, nz);
+  if (n.world <= 1 || !n.comm) return 0;
   char* b = (char*)plane0;
   KB_TRY(nccl_check(n.GroupStart(), "ncclGroupStart"));
   if (n.rank > 0) {
@@ -148,10 +199,14 @@ static int exchange_planes(void* plane0, size_t plane_bytes, int nz, cudaStream_
   KB_TRY(nccl_check(n.GroupEnd(), "ncclGroupEnd"));
   return 0;
 }
+static int level_field(int level, int which) { return HF_LEVEL0 + 6 * level + which; }
 
+// complete a replicated array of the level pool: src = my slice inside my copy dst
 static int allgather_f32(const float* src, float* dst, size_t count) {
-  Nccl& n = ctx().nccl;
-  return nccl_check(n.AllGather(src, dst, count, /*ncclFloat32*/ 7, n.comm, ctx().st), "ncclAllGather");
+  Ctx& c = ctx();
+  if (c.link.p2p) return link_gather(c, (const char*)src, count * sizeof(float));
+  Nccl& n = c.nccl;
+  return nccl_check(n.AllGather(src, dst, count, /*ncclFloat32*/ 7, n.comm, c.st), "ncclAllGather");
 }
 
 // ---- stencil launcher ---------------------------------------------------------------------------
@@ -192,12 +247,8 @@ static int make_tmap_code(CUtensorMap* tm, uint8_t* code, const Dom& D) {
 }
 
 template <int MODE>
-static int ws_prepare() {
-  static bool done = false;
-  if (!done) {
-    KB_CUDA(cudaFuncSetAttribute(k_stencil_ws<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
-    done = true;
-  }
+static int ws_prepare() {  // function attributes are per device: applied on every setup (cheap)
+  KB_CUDA(cudaFuncSetAttribute(k_stencil_ws<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
   return 0;
 }
 
@@ -362,15 +413,26 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
     if (k >= 1) mg.nu0 = k;
   }
   Nccl& nc = c.nccl;
-  mg.dist = c.dist_active && nc.world > 1;
+  mg.dist = c.dist_active && (c.link.p2p ? c.link.world : nc.world) > 1;
   mg.lo = mg.dist && D.z0 > 0;
   mg.hi = mg.dist && D.z0 + D.nz < D.nzg;
   // z-slabs: an aggregate must not straddle two ranks, so z is coarsened only while every rank's first
   // plane and plane count are even; equal slabs are required (the dense level is all-gathered)
   int kz = 1 << 20;
-  if (mg.dist) {
+  auto even_depth = [](int z0, int nz) {
     int k = 0;
-    while (((D.z0 >> k) & 1) == 0 && ((D.nz >> k) & 1) == 0 && (D.nz >> k) > 1) k++;
+    while (((z0 >> k) & 1) == 0 && ((nz >> k) & 1) == 0 && (nz >> k) > 1) k++;
+    return k;
+  };
+  if (mg.dist && c.link.p2p) {
+    // every rank's slab geometry arrived with the window tables (link_publish): no collective needed
+    for (int r = 0; r < c.link.world; r++) {
+      const WinTable& o = c.link.h_win[r];
+      if (o.nz != D.nz) return 0;  // unequal slabs: stay on the diagonally preconditioned path
+      kz = std::min(kz, even_depth(o.z0, o.nz));
+    }
+  } else if (mg.dist) {
+    const int k = even_depth(D.z0, D.nz);
     c.hS->tmp[0] = k;
     c.hS->tmp[1] = D.nz;
     c.hS->tmp[2] = -D.nz;
@@ -444,7 +506,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   mg.nlev = l;
   mg.ndense = mg.L[l].nx * mg.L[l].ny * nzg;
   if (floats > c.cap_mg) {
-    if (c.mg_pool) cudaFree(c.mg_pool);
+    link_release_window(c, W_POOL, c.mg_pool);
     c.mg_pool = nullptr;
     c.cap_mg = 0;
     KB_CUDA(cudaMalloc(&c.mg_pool, floats * sizeof(float)));
@@ -452,9 +514,33 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   }
   if (!c.mg_inv) KB_CUDA(cudaMalloc(&c.mg_inv, (size_t)MG_DENSE_MAX * MG_DENSE_MAX * sizeof(double)));
   if (!c.mg_tab) KB_CUDA(cudaMalloc(&c.mg_tab, (size_t)2 * MG_TAB * sizeof(float)));
+  mg.pitch = mg_pitch(D.nx);
+  {
+    const size_t need = (size_t)mg.pitch * D.ny * (D.nz + 2);
+    if (mg.nu0 >= 2 && need > c.cap_xf) {
+      for (int k = 0; k < 2; k++) {
+        link_release_window(c, k == 0 ? W_XF0 : W_XF1, c.xf[k]);
+        c.xf[k] = nullptr;
+      }
+      c.cap_xf = 0;
+      for (int k = 0; k < 2; k++) KB_CUDA(cudaMalloc(&c.xf[k], need * sizeof(float)));
+      c.cap_xf = need;
+    }
+  }
+  // Everything a neighbour may store into once the group has met must be zeroed BEFORE the meeting: a fast
+  // neighbour pushes its first halo planes while this rank is still setting up.
+  KB_CUDA(cudaMemsetAsync(c.mg_pool, 0, floats * sizeof(float), c.st));
+  {
+    const size_t uplane = (size_t)mg.pitch * D.ny, need = uplane * (D.nz + 2);
+    KB_CUDA(cudaMemsetAsync(c.u, 0, uplane * sizeof(float), c.st));
+    KB_CUDA(cudaMemsetAsync(c.u + uplane * (D.nz + 1), 0, uplane * sizeof(float), c.st));
+    if (mg.nu0 >= 2)
+      for (int k = 0; k < 2; k++) KB_CUDA(cudaMemsetAsync(c.xf[k], 0, need * sizeof(float), c.st));
+  }
+  // the level pool and the iterate fields may just have moved: the neighbours need their new addresses
+  if (mg.dist && c.link.p2p) KB_TRY(link_publish(c, D, false));
   k_mg_tables<<<(MG_TAB + 255) / 256, 256, 0, c.st>>>(c.mg_tab, C, D.nzg == 1);
   KB_LAUNCHED();
-  KB_CUDA(cudaMemsetAsync(c.mg_pool, 0, floats * sizeof(float), c.st));
   float* base = c.mg_pool;
   for (int k = 1; k <= mg.nlev; k++) {
     MgLevel& L = mg.L[k];
@@ -493,39 +579,23 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
       KB_TRY(allgather_f32(T.cz, L.cz, cnt));
       KB_TRY(allgather_f32(T.wsum, L.wsum, cnt));
     }
-    if (!rep_k) KB_TRY(exchange_planes(L.cz, pb, L.nz, c.st));  // cz[-1]: the face towards the lower neighbour
+    if (!rep_k) KB_TRY(exchange_planes(level_field(k, HL_CZ), W_POOL, L.cz, pb, L.nz, c.st));  // cz[-1]: the face towards the lower neighbour
     k_mg_dinv<<<mg_grid((long)L.nx * L.ny * L.nz), 256, 0, c.st>>>(L, rep_k ? 0 : (int)mg.lo);
     KB_LAUNCHED();
-    if (!rep_k) KB_TRY(exchange_planes(L.dinv, pb, L.nz, c.st));
+    if (!rep_k) KB_TRY(exchange_planes(level_field(k, HL_DINV), W_POOL, L.dinv, pb, L.nz, c.st));
   }
   k_mg_dense_setup<<<1, MG_DENSE_MAX, 0, c.st>>>(mg.L[mg.nlev], c.mg_inv);
   KB_LAUNCHED();
   KB_CUDA(cudaGetLastError());
   // voxel-grid passes: tensor maps on u and the iterate fields, work plan (z chunks of even length so
   // aggregates stay whole)
-  mg.pitch = mg_pitch(D.nx);
   {
-    const size_t uplane = (size_t)mg.pitch * D.ny, need = uplane * (D.nz + 2);
-    if (mg.nu0 >= 2 && need > c.cap_xf) {
-      for (int k = 0; k < 2; k++) {
-        if (c.xf[k]) cudaFree(c.xf[k]);
-        c.xf[k] = nullptr;
-      }
-      c.cap_xf = 0;
-      for (int k = 0; k < 2; k++) KB_CUDA(cudaMalloc(&c.xf[k], need * sizeof(float)));
-      c.cap_xf = need;
-    }
+    const size_t uplane = (size_t)mg.pitch * D.ny;
     float* fields[3] = {c.u, mg.nu0 >= 2 ? c.xf[0] : nullptr, mg.nu0 >= 2 ? c.xf[1] : nullptr};
     CUtensorMap* maps[3] = {&mg.tm_u, &mg.tm_x[0], &mg.tm_x[1]};
     for (int k = 0; k < 3; k++) {
       if (!fields[k]) continue;
-      // the halo planes stay zero at the global ends; the row padding of the iterates is never written
-      if (k == 0) {
-        KB_CUDA(cudaMemsetAsync(fields[k], 0, uplane * sizeof(float), c.st));
-        KB_CUDA(cudaMemsetAsync(fields[k] + uplane * (D.nz + 1), 0, uplane * sizeof(float), c.st));
-      } else {
-        KB_CUDA(cudaMemsetAsync(fields[k], 0, need * sizeof(float), c.st));
-      }
+      // (halo planes and row padding were zeroed before the group met, above)
       cuuint64_t dims[3] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nz + 2};
       cuuint64_t strides[2] = {(cuuint64_t)mg.pitch * 4, (cuuint64_t)uplane * 4};
       cuuint32_t box[3] = {MG_BOXW, BOXH, 1};
@@ -610,7 +680,9 @@ static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass&
   }
 #undef KB_FINE
   KB_LAUNCHED();
-  if (out >= 0) KB_TRY(exchange_planes(c.xf[out] + uplane, uplane * sizeof(float), mg.D.nz, c.st));
+  if (out >= 0)
+    KB_TRY(exchange_planes(out == 0 ? HF_XF0 : HF_XF1, out == 0 ? W_XF0 : W_XF1, c.xf[out] + uplane, uplane * sizeof(float), mg.D.nz,
+                           c.st));
   return 0;
 }
 
@@ -623,7 +695,7 @@ static int mg_vcycle(const Mg& mg, float* z) {
   const int lo = mg.lo, hi = mg.hi, nu = mg.nu, nu0 = mg.nu0;
   const float* w = mg.om;
   const float* w0 = mg.om0;
-  KB_TRY(exchange_planes(c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
+  KB_TRY(exchange_planes(HF_U, W_U, c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
   // ---- voxel grid, down ----
   int cur = 0;  // field holding the current iterate (0 = u, scaled by w_1)
   float sc = w0[0];
@@ -656,7 +728,7 @@ static int mg_vcycle(const Mg& mg, float* z) {
     const size_t on = nslice ? (size_t)mg.z0_la * N.nx * N.ny : 0;
     const int nnz = nslice ? mg.nzl_la : N.nz;
     const dim3 gl = mg_row_grid(L.nx, L.ny, L.nz), gn = mg_row_grid(N.nx, N.ny, nnz);
-    if (!rep) KB_TRY(exchange_planes(L.u, pb, L.nz, c.st));
+    if (!rep) KB_TRY(exchange_planes(level_field(l, HL_U), W_POOL, L.u, pb, L.nz, c.st));
     const float* in = L.u;
     float s1 = w[0];
     for (int k = 1; k < nu; k++) {
@@ -664,7 +736,7 @@ static int mg_vcycle(const Mg& mg, float* z) {
       k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, MgPass{s1, 1.f - w[k], w[k], w[k]}, L.fx, L.fy, L.fz,
                                           N.nx, N.ny, out, llo, lhi, mg_bx(L.nx), c.S);
       KB_LAUNCHED();
-      if (!rep) KB_TRY(exchange_planes(out, pb, L.nz, c.st));
+      if (!rep) KB_TRY(exchange_planes(level_field(l, out == L.t0 ? HL_T0 : HL_T1), W_POOL, out, pb, L.nz, c.st));
       in = out;
       s1 = 1.f;
     }
@@ -702,7 +774,7 @@ static int mg_vcycle(const Mg& mg, float* z) {
         k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, llo, lhi,
                                             mg_bx(L.nx), c.S);
       KB_LAUNCHED();
-      if (!rep) KB_TRY(exchange_planes(out, pb, L.nz, c.st));
+      if (!rep) KB_TRY(exchange_planes(level_field(l, out == L.e ? HL_E : (out == L.t0 ? HL_T0 : HL_T1)), W_POOL, out, pb, L.nz, c.st));
       in = out;
       s1 = 1.f;
     }
@@ -731,6 +803,14 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   if (!(P.ks > 0) || !(P.kf > 0)) return fail(KEFFB200_EINVAL, "conductivities must be positive");
   KB_TRY(ensure_ws(D));
   const size_t plane = (size_t)D.nx * D.ny, n = plane * D.nz;
+  // halo planes of the two stencil inputs start at zero (global ends keep them: zero coefficient)
+  KB_CUDA(cudaMemsetAsync(c.x, 0, plane * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.x + plane * (D.nz + 1), 0, plane * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.p, 0, plane * 8, c.st));
+  KB_CUDA(cudaMemsetAsync(c.p + plane * (D.nz + 1), 0, plane * 8, c.st));
+  // z-slabs over peer memory: meet the group (everybody has finished its previous solve), clear my arrival
+  // counters, publish where my workspace lives and learn where the neighbours' does
+  if (c.dist_active && c.link.p2p) KB_TRY(link_publish(c, D, true));
   const Coef C = make_coef(D.nx, D.ny, D.nzg, P);
   const bool lo = c.dist_active && D.z0 > 0, hi = c.dist_active && D.z0 + D.nz < D.nzg;
   double *x = c.x + plane, *r = c.r + plane, *p = c.p + plane, *q = c.q + plane;
@@ -743,11 +823,6 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   KB_CUDA(cudaEventRecord(c.ev0, c.st));
   k_make_code<<<c.sms * 8, 256, 0, c.st>>>(d_mask_halo + plane, c.code, D, lo, hi);
   KB_LAUNCHED();
-  // halo planes of the two stencil inputs start at zero (global ends keep them: zero coefficient)
-  KB_CUDA(cudaMemsetAsync(c.x, 0, plane * 8, c.st));
-  KB_CUDA(cudaMemsetAsync(c.x + plane * (D.nz + 1), 0, plane * 8, c.st));
-  KB_CUDA(cudaMemsetAsync(c.p, 0, plane * 8, c.st));
-  KB_CUDA(cudaMemsetAsync(c.p + plane * (D.nz + 1), 0, plane * 8, c.st));
   if (d_Tinit) {
     KB_CUDA(cudaMemcpyAsync(x, d_Tinit, n * 8, cudaMemcpyDeviceToDevice, c.st));
   } else {
@@ -760,7 +835,9 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   if (mg_eligible(D, P.flags)) KB_TRY(mg_setup(mg, D, C));
   const long n2 = (long)(n / 2);
   const int gm = mg_grid(n2);
-  const long check_every = mg.on ? std::min<long>(P.check_every, 2) : P.check_every;
+  // iterations between two convergence records.  The multigrid path takes ~10 iterations of milliseconds: it
+  // records every iteration; the diagonally preconditioned path takes thousands of short ones.
+  const long batch_len = mg.on ? 1 : P.check_every;
 
   Scal h0;
   memset(&h0, 0, sizeof h0);
@@ -771,112 +848,118 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   *c.hS = h0;
   KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
 
-  long total_iters = 0;
-  double keff_prev = NAN, keff = NAN, ql = 0, qr = 0;
+  // (re)start: r = b - A x, p = z = M r
+  auto enqueue_init = [&]() -> int {
+    KB_TRY(exchange_halo(c.x, D, c.st));
+    if (mg.on) KB_TRY(stencil_launch<MODE_INIT_R>(s, 0, r, nullptr));  // the cycle builds z itself
+    else KB_TRY(stencil_launch<MODE_INIT>(s, 0, r, p));
+    KB_TRY(reduce_step<RS_INIT>(s.grid, 0));
+    if (mg.on) {  // p = z = M r, r.z
+      KB_TRY(mg_make_u(mg, r));
+      KB_TRY(mg_vcycle(mg, c.z));
+      KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, 0));
+      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1);
+      KB_LAUNCHED();
+    }
+    return 0;
+  };
+  // iteration k since the last (re)start; every kernel returns at once when the stop flag is up
+  auto enqueue_iter = [&](long k) -> int {
+    const int par = (int)(k & 1);
+    KB_TRY(exchange_halo(c.p, D, c.st));
+    KB_TRY(stencil_launch<MODE_APPLY>(s, 1, q, nullptr));
+    KB_TRY(reduce_step<RS_PQ>(s.grid, 0));
+    if (mg.on) {
+      k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(r, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D, c.S, par,
+                                                c.partials);
+      KB_LAUNCHED();
+      KB_TRY(reduce_step<RS_RR_MG>(mg.gu, 0));
+      KB_TRY(mg_vcycle(mg, c.z));
+      KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, par ^ 1));
+      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0);
+      KB_LAUNCHED();
+      return 0;
+    }
+    if (V == 2) k_cg_update<2><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
+    else k_cg_update<1><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
+    KB_LAUNCHED();
+    KB_TRY(reduce_step<RS_ITER>(gv, par));
+    if (V == 2) k_cg_dir<2><<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
+    else k_cg_dir<1><<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
+    KB_LAUNCHED();
+    return 0;
+  };
+  // convergence record `slot`: wall fluxes (computed only once the stop flag is up -- they are part of the stop
+  // rule, not of the iteration), then the scalars travel to pinned memory; the host reads them one record behind
+  auto enqueue_record = [&](int slot, bool force_flux) -> int {
+    k_flux<<<gf, 256, 0, c.st>>>(x, c.code, C, D, nullptr, nullptr, c.partials, force_flux ? nullptr : c.S);
+    KB_LAUNCHED();
+    KB_TRY(reduce_step<RS_FLUX>(gf, force_flux ? 1 : 0));
+    KB_CUDA(cudaMemcpyAsync(&c.hring[slot], c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
+    KB_CUDA(cudaEventRecord(c.evb[slot], c.st));
+    return 0;
+  };
+
+  long total_iters = 0;  // iterations of the (re)starts already closed
+  double keff = NAN, ql = 0, qr = 0;
   int status = 1;
-  bool need_init = true;
-  long k = 0;  // host-side iteration index since the last (re)start
-  while (true) {
-    if (need_init) {
-      KB_TRY(exchange_halo(c.x, D, c.st));
-      if (mg.on) KB_TRY(stencil_launch<MODE_INIT_R>(s, 0, r, nullptr));  // the cycle builds z itself
-      else KB_TRY(stencil_launch<MODE_INIT>(s, 0, r, p));
-      k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 2, c.S);
-      KB_LAUNCHED();
-      KB_TRY(allreduce_tmp(c.S->tmp, 3));
-      k_step_init<<<1, 1, 0, c.st>>>(c.S);
-      KB_LAUNCHED();
-      if (mg.on) {  // p = z = M r, r.z
-        KB_TRY(mg_make_u(mg, r));
-        KB_TRY(mg_vcycle(mg, c.z));
-        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
-        KB_LAUNCHED();
-        KB_TRY(allreduce_tmp(c.S->tmp, 1));
-        k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, 0);
-        KB_LAUNCHED();
-        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1);
-        KB_LAUNCHED();
+  bool finished = false;
+  while (!finished) {
+    KB_TRY(enqueue_init());
+    long queued = 0;         // iterations enqueued since this (re)start
+    int head = 0, tail = 0;  // records enqueued / read
+    while (true) {
+      // two records in flight: the device never waits for the host
+      while (head - tail < 2 && (head == 0 || total_iters + queued < P.max_iter)) {
+        const long len = std::min<long>(batch_len, P.max_iter - total_iters - queued);
+        for (long i = 0; i < len; i++) KB_TRY(enqueue_iter(queued + i));
+        queued += std::max<long>(len, 0);
+        const bool last = total_iters + queued >= P.max_iter;
+        KB_TRY(enqueue_record(head & 1, last));
+        head++;
       }
-      need_init = false;
-      k = 0;
-    }
-    const long batch = std::min<long>(check_every, P.max_iter - total_iters - k);
-    for (long i = 0; i < batch; i++, k++) {
-      const int par = (int)(k & 1);
-      KB_TRY(exchange_halo(c.p, D, c.st));
-      KB_TRY(stencil_launch<MODE_APPLY>(s, 1, q, nullptr));
-      k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 0, c.S);
-      KB_LAUNCHED();
-      KB_TRY(allreduce_tmp(&c.S->pq, 1));
-      if (mg.on) {
-        k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(r, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D, c.S, par,
-                                                  c.partials);
-        KB_LAUNCHED();
-        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.gu, 1, c.S);
-        KB_LAUNCHED();
-        KB_TRY(allreduce_tmp(c.S->tmp, 2));
-        k_step_mg_rr<<<1, 1, 0, c.st>>>(c.S);
-        KB_LAUNCHED();
-        KB_TRY(mg_vcycle(mg, c.z));
-        k_finalize<<<1, 1024, 0, c.st>>>(c.partials, mg.grid, 5, c.S);
-        KB_LAUNCHED();
-        KB_TRY(allreduce_tmp(c.S->tmp, 1));
-        k_step_mg_rz<<<1, 1, 0, c.st>>>(c.S, par ^ 1);
-        KB_LAUNCHED();
-        k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0);
-        KB_LAUNCHED();
-        continue;
+      KB_CUDA(cudaEventSynchronize(c.evb[tail & 1]));
+      const Scal rec = c.hring[tail & 1];
+      tail++;
+      if (rec.fault) {
+        cudaStreamSynchronize(c.st);
+        return fail(KEFFB200_ENCCL, "a z-slab neighbour never delivered (peer-memory wait timed out)");
       }
-      if (V == 2) k_cg_update<2><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
-      else k_cg_update<1><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
-      KB_LAUNCHED();
-      k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gv, 1, c.S);
-      KB_LAUNCHED();
-      KB_TRY(allreduce_tmp(c.S->tmp, 2));
-      k_step_iter<<<1, 1, 0, c.st>>>(c.S, par);
-      KB_LAUNCHED();
-      if (V == 2) k_cg_dir<2><<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
-      else k_cg_dir<1><<<gv, vt, 0, c.st>>>(p, r, c.code, C, D, c.S, par);
-      KB_LAUNCHED();
-    }
-    // host-visible check: flux, Keff, flags
-    k_flux<<<gf, 256, 0, c.st>>>(x, c.code, C, D, nullptr, nullptr, c.partials);
-    KB_LAUNCHED();
-    k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gf, 4, c.S);
-    KB_LAUNCHED();
-    KB_TRY(allreduce_tmp(c.S->tmp, 2));
-    k_step_flux<<<1, 1, 0, c.st>>>(c.S);
-    KB_LAUNCHED();
-    KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
-    KB_CUDA(cudaStreamSynchronize(c.st));
-    ql = c.hS->ql;
-    qr = c.hS->qr;
-    keff = (ql + qr) / 2 / (P.tr - P.tl);
-    const double imb = fabs(ql - qr) / fabs(keff);
-    // field is frozen once `done` is set, so the reference's "Keff change between checks" is 0 then
-    const double dk = c.hS->done ? 0.0 : fabs((keff - keff_prev) / keff_prev);
-    keff_prev = keff;
-    const long its_now = total_iters + c.hS->it;
-    if (!std::isfinite(keff)) return fail(KEFFB200_ECUDA, "solver produced a non-finite Keff");
-    if (c.hS->done) {
-      if ((imb <= P.flux_balance && dk <= P.convergence) || thr < 1e-14) {
-        status = 0;
+      const long its_now = total_iters + rec.it;
+      if (rec.done) {
+        KB_CUDA(cudaStreamSynchronize(c.st));  // whatever was queued behind this record has returned at once
+        ql = rec.ql;
+        qr = rec.qr;
+        keff = (ql + qr) / 2 / (P.tr - P.tl);
+        if (!std::isfinite(keff)) return fail(KEFFB200_ECUDA, "solver produced a non-finite Keff");
+        const double imb = fabs(ql - qr) / fabs(keff);
         total_iters = its_now;
+        if (imb <= P.flux_balance || thr < 1e-14) {
+          status = 0;
+          finished = true;
+          break;
+        }
+        if (total_iters >= P.max_iter) {
+          finished = true;
+          break;
+        }
+        // residual target met but the two wall fluxes still disagree: tighten and restart CG from x
+        thr *= 0.01;
+        *c.hS = rec;
+        c.hS->thr2 = thr * thr;
+        c.hS->done = 0;
+        KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
         break;
       }
-      // residual target met but the two wall fluxes still disagree: tighten and restart CG from x
-      thr *= 0.01;
-      total_iters = its_now;
-      c.hS->thr2 = thr * thr;
-      c.hS->done = 0;
-      KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
-      need_init = true;
-      if (total_iters >= P.max_iter) break;
-      continue;
-    }
-    if (its_now >= P.max_iter) {
-      total_iters = its_now;
-      break;
+      if (tail == head && its_now >= P.max_iter) {  // iteration cap: the last record carries the fluxes
+        ql = rec.ql;
+        qr = rec.qr;
+        keff = (ql + qr) / 2 / (P.tr - P.tl);
+        if (!std::isfinite(keff)) return fail(KEFFB200_ECUDA, "solver produced a non-finite Keff");
+        total_iters = its_now;
+        finished = true;
+        break;
+      }
     }
   }
 
@@ -884,12 +967,10 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   KB_CUDA(cudaMemsetAsync(&c.S->done, 0, sizeof(int), c.st));
   KB_TRY(exchange_halo(c.x, D, c.st));
   KB_TRY(stencil_launch<MODE_RESID>(s, 0, nullptr, nullptr));
-  k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 3, c.S);
-  KB_LAUNCHED();
-  KB_TRY(allreduce_tmp(c.S->tmp, 3));
+  KB_TRY(reduce_step<RS_RESID>(s.grid, 0));
   KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
   if (d_qL || d_qR) {
-    k_flux<<<gf, 256, 0, c.st>>>(x, c.code, C, D, d_qL, d_qR, c.partials);
+    k_flux<<<gf, 256, 0, c.st>>>(x, c.code, C, D, d_qL, d_qR, c.partials, nullptr);
     KB_LAUNCHED();
   }
   if (d_Tout) KB_CUDA(cudaMemcpyAsync(d_Tout, x, n * 8, cudaMemcpyDeviceToDevice, c.st));
@@ -946,11 +1027,18 @@ static int need_ready() {
 
 using namespace kb;
 
+// number of contexts in use: 1 after keffb200_init, n after keffb200_init_multi(n)
+static int g_nctx = 0;
+
 extern "C" {
 
 const char* keffb200_version(void) { return "keffb200 0.1 (sm_100a)"; }
 const char* keffb200_last_error(void) { return ctx().err.c_str(); }
-long keffb200_launch_count(void) { return ctx().launches; }
+long keffb200_launch_count(void) {
+  long n = 0;
+  for (int i = 0; i < std::max(g_nctx, 1); i++) n += ctx_table()[i].launches;
+  return n;
+}
 
 void keffb200_default_params(keffb200_params* p) {
   memset(p, 0, sizeof *p);
@@ -960,16 +1048,13 @@ void keffb200_default_params(keffb200_params* p) {
   p->tr = 1;
   p->convergence = 1e-5;
   p->max_iter = 500000;
-  p->rel_residual = 1e-8;
-  p->flux_balance = 1e-6;
+  p->rel_residual = 0;  /* 0 = derived from `convergence`: 1e-8 at the shipped 1e-5 */
+  p->flux_balance = 0;  /* 0 = derived from `convergence`: 1e-6 at the shipped 1e-5 */
   p->check_every = 32;
   p->flags = 0;
 }
 
-int keffb200_init(int device) {
-  Ctx& c = ctx();
-  if (c.ready && c.device == device) return 0;
-  if (c.ready) keffb200_shutdown();
+static int init_context(Ctx& c, int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(KEFFB200_ENOGPU, "no CUDA device visible: this library has no CPU path");
@@ -993,7 +1078,10 @@ int keffb200_init(int device) {
   for (int k = 0; k < 3; k++) KB_CUDA(cudaEventCreateWithFlags(&c.evp[k], cudaEventDisableTiming));
   KB_CUDA(cudaMalloc(&c.partials, (size_t)PARTIAL_SLOTS * 3 * sizeof(double)));
   KB_CUDA(cudaMalloc(&c.S, sizeof(Scal)));
+  KB_CUDA(cudaMemset(c.S, 0, sizeof(Scal)));
   KB_CUDA(cudaMallocHost(&c.hS, sizeof(Scal)));
+  KB_CUDA(cudaMallocHost(&c.hring, 2 * sizeof(Scal)));
+  for (int k = 0; k < 2; k++) KB_CUDA(cudaEventCreateWithFlags(&c.evb[k], cudaEventDisableTiming));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
@@ -1006,12 +1094,11 @@ int keffb200_init(int device) {
   return 0;
 }
 
-void keffb200_shutdown(void) {
-  Ctx& c = ctx();
+static void destroy_context(Ctx& c) {
   if (!c.ready) return;
-  keffb200_dist_shutdown();
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
+  link_free(c);
   for (double** f : {&c.x, &c.r, &c.p, &c.q, &c.qL, &c.qR, &c.partials}) {
     if (*f) cudaFree(*f);
     *f = nullptr;
@@ -1044,6 +1131,13 @@ void keffb200_shutdown(void) {
   for (int k = 0; k < 3; k++) cudaEventDestroy(c.evp[k]);
   if (c.S) cudaFree(c.S);
   if (c.hS) cudaFreeHost(c.hS);
+  if (c.hring) cudaFreeHost(c.hring);
+  c.hring = nullptr;
+  for (int k = 0; k < 2; k++) {
+    if (c.evb[k]) cudaEventDestroy(c.evb[k]);
+    c.evb[k] = nullptr;
+  }
+  c.attr_batch = c.attr_ws = false;
   c.code = c.mask = nullptr;
   c.batch_ws = nullptr;
   c.S = c.hS = nullptr;
@@ -1059,14 +1153,112 @@ void keffb200_shutdown(void) {
   c.ready = false;
 }
 
-int keffb200_solve3d(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T_init,
-                     double* T_out, double* qL, double* qR, keffb200_result* out) {
-  KB_TRY(need_ready());
-  if (!solid || !out) return fail(KEFFB200_EINVAL, "null argument");
+int keffb200_init(int device) {
+  Ctx& c = ctx_table()[0];
+  if (c.ready && g_nctx == 1 && c.device == device) return 0;
+  if (g_nctx > 0) keffb200_shutdown();
+  KB_TRY(init_context(c, device));
+  g_nctx = 1;
+  return 0;
+}
+
+int keffb200_init_multi(int n_gpus) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(KEFFB200_ENOGPU, "no CUDA device visible: this library has no CPU path");
+  if (n_gpus <= 0) n_gpus = ndev;
+  if (n_gpus > ndev || n_gpus > KB_MAX_GPUS || n_gpus > KB_MAX_RANKS)
+    return fail(KEFFB200_EINVAL, "%d GPUs requested, %d visible (at most %d per process)", n_gpus, ndev, KB_MAX_RANKS);
+  if (g_nctx == n_gpus && ctx_table()[0].ready && (n_gpus == 1 || ctx_table()[0].link.world == n_gpus)) return 0;
+  if (g_nctx > 0) keffb200_shutdown();
+  Ctx* T = ctx_table();
+  for (int i = 0; i < n_gpus; i++) {
+    const int rc = init_context(T[i], i);
+    if (rc != 0) {
+      if (i > 0) T[0].err = T[i].err.empty() ? T[0].err : T[i].err;
+      return rc;
+    }
+  }
+  g_nctx = n_gpus;
+  if (n_gpus > 1) {
+    // one slab group inside the process: every GPU maps every other GPU's memory (NVLink peer access)
+    bool all = true;
+    for (int i = 0; i < n_gpus && all; i++)
+      for (int j = 0; j < n_gpus && all; j++) {
+        int can = 1;
+        if (i != j) cudaDeviceCanAccessPeer(&can, i, j);
+        all = can != 0;
+      }
+    if (!all) return fail(KEFFB200_ECUDA, "GPUs 0..%d cannot all access each other's memory", n_gpus - 1);
+    for (int i = 0; i < n_gpus; i++) {
+      KB_CUDA(cudaSetDevice(i));
+      for (int j = 0; j < n_gpus; j++) {
+        if (i == j) continue;
+        const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return fail(KEFFB200_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", i, j, cudaGetErrorString(e));
+      }
+      T[i].link.rank = i;
+      T[i].link.world = n_gpus;
+      KB_TRY(link_alloc_mail(T[i]));
+    }
+    for (int i = 0; i < n_gpus; i++) {
+      for (int j = 0; j < n_gpus; j++) T[i].link.mail[j] = T[j].link.mail[j];
+      T[i].link.p2p = true;
+    }
+  }
+  KB_CUDA(cudaSetDevice(0));
+  return 0;
+}
+
+int keffb200_device_count(void) { return g_nctx; }
+
+void keffb200_shutdown(void) {
+  Ctx* T = ctx_table();
+  if (g_nctx == 0 && !T[0].ready) return;
+  keffb200_dist_shutdown();
+  for (int i = 0; i < KB_MAX_GPUS; i++) destroy_context(T[i]);
+  g_nctx = 0;
+}
+
+}  // extern "C"
+
+// run fn(i) on context i (i < n), one host thread per GPU; the first error wins and lands in context 0
+template <class F>
+static int fan_out(int n, F fn) {
+  std::vector<std::thread> th;
+  std::vector<int> rc(n, 0);
+  Ctx* T = ctx_table();
+  for (int i = 0; i < n; i++)
+    th.emplace_back([&, i] {
+      ctx_current() = &T[i];
+      if (cudaSetDevice(T[i].device) != cudaSuccess) rc[i] = fail(KEFFB200_ECUDA, "cudaSetDevice(%d) failed", T[i].device);
+      else rc[i] = fn(i);
+      ctx_current() = nullptr;
+    });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; i++)
+    if (rc[i] != 0) {
+      if (i > 0) T[0].err = T[i].err;
+      return rc[i];
+    }
+  return 0;
+}
+
+// contiguous shares of n units over `parts` owners, sizes differing by at most one
+static void share(long n, int part, int parts, long* first, long* count) {
+  const long base = n / parts, rem = n % parts;
+  *count = base + (part < rem ? 1 : 0);
+  *first = part * base + std::min<long>(part, rem);
+}
+
+static long g_slab_min_cells = 1L << 26;  // volumes below this are solved on one GPU even when more are bound
+static unsigned long long g_epoch = 0;    // fan-outs so far: ranks of a sub-group agree on barrier numbers through it
+
+static int solve3d_one(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params& P, const double* T_init,
+                       double* T_out, double* qL, double* qR, keffb200_result* out) {
   Ctx& c = ctx();
-  const keffb200_params P = norm_params(p);
   Dom D{nx, ny, nz, 0, nz};
-  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
   KB_TRY(stage_mask(solid, false, D));
   const size_t n = (size_t)nx * ny * nz;
   double* dT = nullptr;
@@ -1083,6 +1275,86 @@ int keffb200_solve3d(const uint8_t* solid, int nx, int ny, int nz, const keffb20
   KB_CUDA(cudaStreamSynchronize(c.st));
   return 0;
 }
+
+// One volume in g z-slabs on the first g GPUs of this process (z is the slowest index, Keff3D/keff3D.h:691: a
+// slab is a contiguous range of the caller's arrays).  Rank i stages its planes plus one structure plane either
+// side, joins the collective solve and copies its part of the outputs back.
+static int solve3d_slabs(int g, const uint8_t* solid, int nx, int ny, int nz, const keffb200_params& P, const double* T_init,
+                         double* T_out, double* qL, double* qR, keffb200_result* out) {
+  Ctx* T = ctx_table();
+  const int world = T[0].link.world;
+  g_epoch++;
+  std::vector<keffb200_result> res(g);
+  const int rc = fan_out(g, [&](int i) -> int {
+    Ctx& c = ctx();
+    long z0 = 0, nzl = 0;
+    share(nz, i, g, &z0, &nzl);
+    Dom D{nx, ny, (int)nzl, (int)z0, nz};
+    const size_t plane = (size_t)nx * ny, n = plane * nzl;
+    c.link.world = g;  // the group of this solve: the first g ranks
+    c.link.bar_seq = g_epoch << 8;
+    int r = ensure_ws(D);
+    if (r == 0) {
+      const long zlo = std::max<long>(z0 - 1, 0), zhi = std::min<long>(z0 + nzl + 1, nz);
+      if (cudaMemsetAsync(c.mask, 0, plane, c.st) != cudaSuccess ||
+          cudaMemsetAsync(c.mask + plane * (nzl + 1), 0, plane, c.st) != cudaSuccess ||
+          cudaMemcpyAsync(c.mask + plane * (zlo - (z0 - 1)), solid + plane * zlo, plane * (zhi - zlo), cudaMemcpyHostToDevice,
+                          c.st) != cudaSuccess)
+        r = fail(KEFFB200_ECUDA, "staging slab %d failed: %s", i, cudaGetErrorString(cudaGetLastError()));
+    }
+    double* dT = nullptr;
+    if (r == 0 && T_init) {
+      dT = c.q + plane;
+      if (cudaMemcpyAsync(dT, T_init + plane * z0, n * 8, cudaMemcpyHostToDevice, c.st) != cudaSuccess)
+        r = fail(KEFFB200_ECUDA, "staging the warm start of slab %d failed", i);
+    }
+    // every rank must enter the collective solve, also one whose staging failed (its result is void anyway)
+    c.dist_active = true;
+    const int rs = solve_grid(c.mask, D, P, dT, nullptr, qL ? c.qL : nullptr, qR ? c.qR : nullptr, &res[i]);
+    c.dist_active = false;
+    c.link.world = world;
+    if (r == 0) r = rs;
+    if (r != 0) return r;
+    if (T_out) KB_CUDA(cudaMemcpyAsync(T_out + plane * z0, c.x + plane, n * 8, cudaMemcpyDeviceToHost, c.st));
+    const size_t rows = (size_t)ny * nzl;
+    if (qL) KB_CUDA(cudaMemcpyAsync(qL + (size_t)ny * z0, c.qL, rows * 8, cudaMemcpyDeviceToHost, c.st));
+    if (qR) KB_CUDA(cudaMemcpyAsync(qR + (size_t)ny * z0, c.qR, rows * 8, cudaMemcpyDeviceToHost, c.st));
+    KB_CUDA(cudaStreamSynchronize(c.st));
+    return 0;
+  });
+  if (rc != 0) return rc;
+  *out = res[0];
+  for (int i = 1; i < g; i++) out->gpu_ms = std::max(out->gpu_ms, res[i].gpu_ms);
+  return 0;
+}
+
+// how many slabs a volume of nz planes gets on up to `avail` GPUs: the largest count that divides nz (equal slabs
+// keep the multigrid path; with an even plane count per slab where possible)
+static int slab_count(int nz, int avail) {
+  int best = 1;
+  for (int g = 2; g <= avail; g++)
+    if (nz % g == 0 && nz / g >= 4) best = g;
+  for (int g = best; g >= 2; g--)
+    if (nz % g == 0 && (nz / g) % 2 == 0 && 2 * g > best) return g;
+  return best;
+}
+
+extern "C" {
+
+int keffb200_solve3d(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T_init,
+                     double* T_out, double* qL, double* qR, keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!solid || !out) return fail(KEFFB200_EINVAL, "null argument");
+  const keffb200_params P = norm_params(p);
+  if (nx < 2 || ny < 1 || nz < 1) return fail(KEFFB200_EINVAL, "grid %dx%dx%d too small", nx, ny, nz);
+  if (g_nctx > 1 && ctx_current() == nullptr && ctx_table()[0].link.p2p && (long)nx * ny * nz >= g_slab_min_cells) {
+    const int g = slab_count(nz, g_nctx);
+    if (g > 1) return solve3d_slabs(g, solid, nx, ny, nz, P, T_init, T_out, qL, qR, out);
+  }
+  return solve3d_one(solid, nx, ny, nz, P, T_init, T_out, qL, qR, out);
+}
+
+void keffb200_set_slab_min_cells(long cells) { g_slab_min_cells = cells < 0 ? (1L << 26) : cells; }
 
 int keffb200_solve2d(const uint8_t* solid, int nx, int ny, const keffb200_params* p, const double* T_init,
                      double* T_out, double* qL, double* qR, keffb200_result* out) {
@@ -1107,13 +1379,18 @@ int keffb200_solve3d_slab_dev(const uint8_t* d_solid_halo, int nx, int ny, int n
   if (!d_solid_halo || !out) return fail(KEFFB200_EINVAL, "null argument");
   KB_TRY(check_dev_ptr(d_solid_halo, "d_solid_halo"));
   if (z0 < 0 || nz_local < 1 || z0 + nz_local > nz_global) return fail(KEFFB200_EINVAL, "bad slab extent");
-  if (ctx().nccl.world > 1 && !ctx().nccl.comm) return fail(KEFFB200_ESTATE, "keffb200_dist_init has not been called");
+  Ctx& c = ctx();
+  const bool group = c.nccl.world > 1 && (c.nccl.comm || c.link.p2p);
+  // a partial slab without a communicator would be solved with adiabatic cut faces and report a wrong Keff
+  if ((z0 > 0 || nz_local < nz_global) && !group)
+    return fail(KEFFB200_ESTATE, "partial slab [%d, %d) of %d planes, but keffb200_dist_init has not been called", z0,
+                z0 + nz_local, nz_global);
   const keffb200_params P = norm_params(p);
   Dom D{nx, ny, nz_local, z0, nz_global};
   KB_TRY(ensure_ws(D));
-  ctx().dist_active = ctx().nccl.world > 1;
+  c.dist_active = group;
   const int rc = solve_grid(d_solid_halo, D, P, nullptr, d_T_out, nullptr, nullptr, out);
-  ctx().dist_active = false;
+  c.dist_active = false;
   return rc;
 }
 
@@ -1125,10 +1402,8 @@ int keffb200_solve2d_batch_dev(const uint8_t* d_solid, int n_img, int nx, int ny
   return batch2d_solve_dev(d_solid, n_img, nx, ny, norm_params(p), d_T_out, out);
 }
 
-int keffb200_solve2d_batch(const uint8_t* solid, int n_img, int nx, int ny, const keffb200_params* p, double* T_out,
-                           keffb200_result* out) {
-  KB_TRY(need_ready());
-  if (!solid || !out || n_img < 1) return fail(KEFFB200_EINVAL, "bad argument");
+static int solve2d_batch_one(const uint8_t* solid, int n_img, int nx, int ny, const keffb200_params& P, double* T_out,
+                             keffb200_result* out) {
   Ctx& c = ctx();
   const size_t n = (size_t)nx * ny, tot = n * n_img;
   if (tot > c.cap_stage) {
@@ -1145,12 +1420,29 @@ int keffb200_solve2d_batch(const uint8_t* solid, int n_img, int nx, int ny, cons
     if (cudaMalloc(&c.stageT, tot * 8) != cudaSuccess) return fail(KEFFB200_ENOMEM, "cannot allocate batch temperature output");
     c.cap_stageT = tot;
   }
-  KB_TRY(batch2d_solve_host(solid, c.stage, n_img, nx, ny, norm_params(p), T_out ? c.stageT : nullptr, out));
+  KB_TRY(batch2d_solve_host(solid, c.stage, n_img, nx, ny, P, T_out ? c.stageT : nullptr, out));
   if (T_out) {
     KB_CUDA(cudaMemcpyAsync(T_out, c.stageT, tot * 8, cudaMemcpyDeviceToHost, c.st));
     KB_CUDA(cudaStreamSynchronize(c.st));
   }
   return 0;
+}
+
+// Images are independent (the reference loops over them, Keff2D/keff2D.cpp:341): with several GPUs bound every GPU
+// takes a contiguous share of the batch on its own host thread -- no communication, results land in place.
+int keffb200_solve2d_batch(const uint8_t* solid, int n_img, int nx, int ny, const keffb200_params* p, double* T_out,
+                           keffb200_result* out) {
+  KB_TRY(need_ready());
+  if (!solid || !out || n_img < 1) return fail(KEFFB200_EINVAL, "bad argument");
+  const keffb200_params P = norm_params(p);
+  const size_t n = (size_t)nx * ny;
+  const int g = (g_nctx > 1 && ctx_current() == nullptr) ? std::min<long>(g_nctx, std::max(1, n_img / 64)) : 1;
+  if (g <= 1) return solve2d_batch_one(solid, n_img, nx, ny, P, T_out, out);
+  return fan_out(g, [&](int i) -> int {
+    long first = 0, count = 0;
+    share(n_img, i, g, &first, &count);
+    return solve2d_batch_one(solid + first * n, (int)count, nx, ny, P, T_out ? T_out + first * n : nullptr, out + first);
+  });
 }
 
 // ---- pieces ------------------------------------------------------------------------------------
@@ -1202,17 +1494,13 @@ int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_p
   KB_CUDA(cudaMemcpyAsync(c.x + plane, T, n * 8, cudaMemcpyHostToDevice, c.st));
   KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
   const int gf = (int)std::min<long>((rows + 255) / 256, (long)c.sms * 4);
-  k_flux<<<gf, 256, 0, c.st>>>(c.x + plane, c.code, C, D, c.qL, c.qR, c.partials);
+  k_flux<<<gf, 256, 0, c.st>>>(c.x + plane, c.code, C, D, c.qL, c.qR, c.partials, nullptr);
   KB_LAUNCHED();
-  k_finalize<<<1, 1024, 0, c.st>>>(c.partials, gf, 4, c.S);
-  KB_LAUNCHED();
-  k_step_flux<<<1, 1, 0, c.st>>>(c.S);
-  KB_LAUNCHED();
+  KB_TRY(reduce_step<RS_FLUX>(gf, 1));
   Stencil s;
   KB_TRY(stencil_setup(s, D, C, P.flags));
   KB_TRY(stencil_launch<MODE_RESID>(s, 0, nullptr, nullptr));
-  k_finalize<<<1, 1024, 0, c.st>>>(c.partials, s.grid, 3, c.S);
-  KB_LAUNCHED();
+  KB_TRY(reduce_step<RS_RESID>(s.grid, 0));
   KB_CUDA(cudaMemcpyAsync(c.hS, c.S, sizeof(Scal), cudaMemcpyDeviceToHost, c.st));
   if (qL) KB_CUDA(cudaMemcpyAsync(qL, c.qL, rows * 8, cudaMemcpyDeviceToHost, c.st));
   if (qR) KB_CUDA(cudaMemcpyAsync(qR, c.qR, rows * 8, cudaMemcpyDeviceToHost, c.st));
@@ -1288,16 +1576,39 @@ int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, con
 // ---- region timer: CUDA events on the library's compute stream -------------------------------
 int keffb200_timer_start(void) {
   KB_TRY(need_ready());
-  KB_CUDA(cudaEventRecord(ctx().evt0, ctx().st));
+  for (int i = 0; i < g_nctx; i++) {
+    Ctx& c = ctx_table()[i];
+    if (g_nctx > 1) KB_CUDA(cudaSetDevice(c.device));
+    KB_CUDA(cudaEventRecord(c.evt0, c.st));
+  }
+  if (g_nctx > 1) KB_CUDA(cudaSetDevice(ctx_table()[0].device));
   return 0;
 }
 
 int keffb200_timer_stop(float* ms) {
   KB_TRY(need_ready());
   if (!ms) return fail(KEFFB200_EINVAL, "null argument");
-  KB_CUDA(cudaEventRecord(ctx().evt1, ctx().st));
-  KB_CUDA(cudaEventSynchronize(ctx().evt1));
-  KB_CUDA(cudaEventElapsedTime(ms, ctx().evt0, ctx().evt1));
+  *ms = 0.f;
+  for (int i = 0; i < g_nctx; i++) {  // several GPUs: the longest of the regions
+    Ctx& c = ctx_table()[i];
+    if (g_nctx > 1) KB_CUDA(cudaSetDevice(c.device));
+    KB_CUDA(cudaEventRecord(c.evt1, c.st));
+    KB_CUDA(cudaEventSynchronize(c.evt1));
+    float t = 0.f;
+    KB_CUDA(cudaEventElapsedTime(&t, c.evt0, c.evt1));
+    *ms = std::max(*ms, t);
+  }
+  if (g_nctx > 1) KB_CUDA(cudaSetDevice(ctx_table()[0].device));
+  return 0;
+}
+
+// Order the library's compute stream behind the work already queued on `stream` (a cudaStream_t; NULL = the
+// legacy default stream): call it before a *_dev entry point whose inputs another stream is still writing.
+int keffb200_wait_stream(void* stream) {
+  KB_TRY(need_ready());
+  Ctx& c = ctx();
+  KB_CUDA(cudaEventRecord(c.evy, (cudaStream_t)stream));
+  KB_CUDA(cudaStreamWaitEvent(c.st, c.evy, 0));
   return 0;
 }
 
@@ -1355,22 +1666,96 @@ int keffb200_comm_id(void* id128) {
   return nccl_check(ctx().nccl.GetUniqueId(id128), "ncclGetUniqueId");
 }
 
+// One process per GPU: map every rank's mailbox through CUDA IPC (the handles travel over the NCCL communicator
+// that was just created -- its only job besides being the fallback).  Every rank must succeed, or all stay on NCCL.
+static int link_bootstrap_ipc(Ctx& c, int rank, int world) {
+  Nccl& n = c.nccl;
+  Link& L = c.link;
+  if (getenv("KEFFB200_SLAB_NCCL")) return 0;  // experiments: keep the NCCL data path
+  if (world > KB_MAX_RANKS) return 0;
+  L.rank = rank;
+  L.world = world;
+  KB_TRY(link_alloc_mail(c));
+  struct Boot {
+    unsigned char handle[64];
+    long long pid;
+    long long ok;
+  };
+  std::vector<Boot> hb(world);
+  Boot mine;
+  memset(&mine, 0, sizeof mine);
+  cudaIpcMemHandle_t h;
+  mine.ok = cudaIpcGetMemHandle(&h, L.mail[rank]) == cudaSuccess;
+  if (mine.ok) memcpy(mine.handle, &h, sizeof h);
+  else cudaGetLastError();
+  mine.pid = (long long)getpid();
+  Boot* db = nullptr;
+  KB_CUDA(cudaMalloc(&db, sizeof(Boot) * world));
+  KB_CUDA(cudaMemcpyAsync(db + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c.st));
+  KB_TRY(nccl_check(n.AllGather(db + rank, db, sizeof(Boot), /*ncclInt8*/ 0, n.comm, c.st), "ncclAllGather"));
+  KB_CUDA(cudaMemcpyAsync(hb.data(), db, sizeof(Boot) * world, cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  bool ok = true;
+  for (int r = 0; r < world && ok; r++) {
+    if (r == rank) continue;
+    void* ptr = nullptr;
+    if (!hb[r].ok || hb[r].pid == mine.pid || link_ipc_open(L.ipc_mail[r], hb[r].handle, 0, &ptr) != 0) ok = false;
+    else L.mail[r] = (Mail*)ptr;
+  }
+  double* flag = (double*)db;
+  const double mine_ok = ok ? 1.0 : 0.0;
+  KB_CUDA(cudaMemcpyAsync(flag, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, c.st));
+  KB_TRY(nccl_check(n.AllReduce(flag, flag, 1, /*ncclFloat64*/ 8, /*ncclMin*/ 3, n.comm, c.st), "ncclAllReduce"));
+  double all_ok = 0;
+  KB_CUDA(cudaMemcpyAsync(&all_ok, flag, sizeof(double), cudaMemcpyDeviceToHost, c.st));
+  KB_CUDA(cudaStreamSynchronize(c.st));
+  cudaFree(db);
+  L.p2p = all_ok > 0.5;
+  L.ipc = L.p2p;
+  if (!L.p2p && getenv("KEFFB200_VERBOSE"))
+    fprintf(stderr, "keffb200: rank %d: peer-memory link unavailable (%s), z-slabs stay on NCCL\n", rank, c.err.c_str());
+  return 0;
+}
+
 int keffb200_dist_init(int rank, int world, const void* id128) {
   KB_TRY(need_ready());
-  Nccl& n = ctx().nccl;
+  Ctx& c = ctx();
+  Nccl& n = c.nccl;
   if (world < 1 || rank < 0 || rank >= world) return fail(KEFFB200_EINVAL, "bad rank/world");
+  if (g_nctx > 1) return fail(KEFFB200_ESTATE, "keffb200_dist_init joins one-GPU processes; this process drives %d GPUs", g_nctx);
   n.rank = rank;
   n.world = world;
   if (world == 1) return 0;
   KB_TRY(nccl_load());
   Id128 id;
   memcpy(id.b, id128, 128);
-  KB_CUDA(cudaSetDevice(ctx().device));
-  return nccl_check(n.CommInitRank(&n.comm, world, id, rank), "ncclCommInitRank");
+  KB_CUDA(cudaSetDevice(c.device));
+  KB_TRY(nccl_check(n.CommInitRank(&n.comm, world, id, rank), "ncclCommInitRank"));
+  return link_bootstrap_ipc(c, rank, world);
 }
 
+// 1 = z-slab halos and reductions travel through peer memory, 0 = through NCCL (or no group)
+int keffb200_dist_peer_memory(void) { return ctx().link.p2p ? 1 : 0; }
+
 void keffb200_dist_shutdown(void) {
-  Nccl& n = ctx().nccl;
+  Ctx& c = ctx();
+  Nccl& n = c.nccl;
+  if (g_nctx <= 1 && c.ready) {
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    if (c.link.p2p && c.link.ipc) {
+      // nobody frees a window before every rank has unmapped it: unmap the workspace windows, meet through the
+      // mailboxes (a rank that shuts down alone waits two seconds, then goes on), unmap the mailboxes, free
+      Link& L = c.link;
+      for (int r = 0; r < KB_MAX_RANKS; r++)
+        for (int w = 0; w < W_COUNT; w++) {
+          if (L.ipcw[r][w].ptr) cudaIpcCloseMemHandle(L.ipcw[r][w].ptr);
+          L.ipcw[r][w].ptr = nullptr;
+        }
+      if (link_barrier(c, 2000000000ull) == 0) cudaStreamSynchronize(c.st);
+    }
+    link_free(c);
+  }
   if (n.comm && n.CommDestroy) n.CommDestroy(n.comm);
   n.comm = nullptr;
   n.rank = 0;

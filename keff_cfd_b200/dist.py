@@ -78,6 +78,11 @@ def init_comm(rank, world, device):
     _comm_ready = True
 
 
+def peer_memory():
+    """True when the slab group exchanges halos and reductions through peer memory (NVLink stores), False on NCCL."""
+    return bool(lib().keffb200_dist_peer_memory())
+
+
 def solve3d_slab(solid_halo_dev, z0, nz_global, params, want_T=False):
     """Collective z-slab solve.  solid_halo_dev: CUDA u8 [nzl+2, ny, nx] (from
     exchange_structure_halos).  Every rank gets the same result record."""
@@ -85,6 +90,7 @@ def solve3d_slab(solid_halo_dev, z0, nz_global, params, want_T=False):
     nzl, ny, nx = solid_halo_dev.shape[0] - 2, solid_halo_dev.shape[1], solid_halo_dev.shape[2]
     T = torch.empty((nzl, ny, nx), dtype=torch.float64, device=solid_halo_dev.device) if want_T else None
     r = Result()
+    _lib.order_after_torch(solid_halo_dev)   # exchange_structure_halos fills the halo planes with asynchronous torch ops
     check(lib().keffb200_solve3d_slab_dev(solid_halo_dev.data_ptr(), nx, ny, nzl, z0, nz_global, C.byref(params),
                                           None if T is None else T.data_ptr(), C.byref(r)))
     d = r.as_dict()

@@ -18,6 +18,7 @@ torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
 r = D.solve3d_slab(halo, z0, nzg, p, want_T=(n <= 128))
 torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
 if rank == 0:
+    print("transport:", "peer-memory" if D.peer_memory() else "nccl")
     print(f"slab {n}x{n}x{nzg} over {world} ranks:", {k: r[k] for k in ("keff", "q_left", "q_right", "rel_residual", "iters", "status", "gpu_ms")}, f"wall {dt:.3f}s")
 if n <= 128:
     parts = [torch.empty_like(r["T"]) for _ in range(world)] if nzg % world == 0 else None
