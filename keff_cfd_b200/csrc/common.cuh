@@ -80,6 +80,15 @@ struct ArLink {
   Mail* mail[KB_MAX_RANKS];  // every rank's mailbox as mapped here (mail[rank] is my own)
 };
 
+// where a producing kernel stores the boundary planes of its output besides its own memory: the halo planes of
+// the z-neighbours (peer addresses, nullptr without a neighbour) and their arrival counters
+struct HaloPush {
+  char* lo_dst;            // the lower neighbour's upper halo plane of the same array
+  char* hi_dst;            // the upper neighbour's lower halo plane
+  unsigned int* lo_flag;   // ... and the counters that tell them it has arrived
+  unsigned int* hi_flag;
+};
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -100,6 +109,15 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 }
 __device__ __forceinline__ void red_add_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// every thread of the CTA has issued its remote stores: make them visible system-wide, then count one arrival
+__device__ __forceinline__ void halo_signal(const HaloPush& H, unsigned int n_lo, unsigned int n_hi) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (H.lo_dst && n_lo) red_add_release_sys(H.lo_flag, n_lo);
+    if (H.hi_dst && n_hi) red_add_release_sys(H.hi_flag, n_hi);
+  }
 }
 constexpr unsigned long long KB_WAIT_NS = 4000000000ull;  // a peer that stays silent this long is gone
 

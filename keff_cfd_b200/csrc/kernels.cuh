@@ -147,7 +147,16 @@ constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
 
 struct Plan {
   int ntx, nty, nzc, zlen, nitems;
+  int bfirst;  // z-slabs: deal the two chunks that touch the slab boundaries first (their planes travel to the
+               // neighbours while the interior chunks are still being worked on)
 };
+__device__ __forceinline__ void plan_item(const Plan& P, int item, int& tx, int& ty, int& zc) {
+  tx = item % P.ntx;
+  const int t1 = item / P.ntx;
+  ty = t1 % P.nty;
+  const int zi = t1 / P.nty;
+  zc = (!P.bfirst || P.nzc < 2) ? zi : (zi == 0 ? 0 : (zi == 1 ? P.nzc - 1 : zi - 1));
+}
 
 __device__ __forceinline__ double pick(bool c, double a, double b) { return c ? a : b; }
 
@@ -175,7 +184,8 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
   const double dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
 
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+    int tx, ty, zc;
+    plan_item(P, item, tx, ty, zc);
     const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
     const int len = min(D.nz, zb + P.zlen) - zb, nplanes = len + 2;
     const int gx = xo + lx, gy = yo + ly;
@@ -374,7 +384,8 @@ __global__ void __launch_bounds__(WS_THR, WS_OCC) k_stencil_ws(const __grid_cons
     if (tid == NTHR) {
       uint32_t seq = 0;
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-        const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+        int tx, ty, zc;
+    plan_item(P, item, tx, ty, zc);
         const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
         const int nplanes = min(D.nz, zb + P.zlen) - zb + 2;
         for (int k = 0; k < nplanes; k++, seq++) {
@@ -400,7 +411,8 @@ __global__ void __launch_bounds__(WS_THR, WS_OCC) k_stencil_ws(const __grid_cons
     const double dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
 
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-      const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+      int tx, ty, zc;
+    plan_item(P, item, tx, ty, zc);
       const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
       const int len = min(D.nz, zb + P.zlen) - zb, nplanes = len + 2;
       const int gx = xo + lx, gy = yo + ly;

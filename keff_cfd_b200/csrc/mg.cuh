@@ -362,12 +362,26 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
                                                      const float* __restrict__ uown, float* __restrict__ fout,
                                                      float* __restrict__ zout, const MgFine M, const MgPass K,
                                                      const Coef C, const Dom D, const Plan P,
-                                                     const Scal* __restrict__ S, double* __restrict__ partials) {
+                                                     const Scal* __restrict__ S, double* __restrict__ partials,
+                                                     const HaloPush H) {
   __shared__ __align__(128) unsigned char tiles[MG_NST * MG_STAGE_STRIDE];
   __shared__ __align__(8) uint64_t full[MG_NST];
   __shared__ float tab[27 * 128];  // OUT 0: d    otherwise: 1/d
   __shared__ double red[32 * 3];
-  if (S->done) return;
+  const bool push = OUT == 1 && (H.lo_dst || H.hi_dst);
+  if (S->done) {
+    if (push) {  // the neighbours count arrivals whether or not the iteration is still running
+      unsigned int nlo = 0, nhi = 0;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        int tx, ty, zc;
+        plan_item(P, item, tx, ty, zc);
+        nlo += zc == 0;
+        nhi += zc == P.nzc - 1;
+      }
+      halo_signal(H, nlo, nhi);
+    }
+    return;
+  }
   const int tid = threadIdx.x, lx = (tid & 31) * 2, ly = (tid >> 5) * 2;
   if (tid == 0) {
     for (int s = 0; s < MG_NST; s++) mbar_init(&full[s], 1);
@@ -384,7 +398,8 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
   const float dfx = (float)C.diff[0], dfy = (float)C.diff[1], dfz = (float)C.diff[2];
 
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    const int tx = item % P.ntx, t1 = item / P.ntx, ty = t1 % P.nty, zc = t1 / P.nty;
+    int tx, ty, zc;
+    plan_item(P, item, tx, ty, zc);
     const int xo = tx * TX, yo = ty * TY, zb = zc * P.zlen;
     const int len = min(D.nz, zb + P.zlen) - zb, nplanes = len + 2;
     const int gx = xo + lx, gy = yo + ly;
@@ -565,6 +580,20 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
         if (OUT == 1) {
           if (row0) *reinterpret_cast<float2*>(fout + cu) = make_float2(za, zb2);
           if (row1) *reinterpret_cast<float2*>(fout + cu + M.pitch) = make_float2(zc2, zd);
+          if (push && (lz == 0 || lz == D.nz - 1)) {
+            // a slab-boundary plane: the same values go straight into the neighbour's halo plane (NVLink stores)
+            const long ro = (long)gy * M.pitch + gx;
+            if (lz == 0 && H.lo_dst) {
+              float* d = reinterpret_cast<float*>(H.lo_dst) + ro;
+              if (row0) *reinterpret_cast<float2*>(d) = make_float2(za, zb2);
+              if (row1) *reinterpret_cast<float2*>(d + M.pitch) = make_float2(zc2, zd);
+            }
+            if (lz == D.nz - 1 && H.hi_dst) {
+              float* d = reinterpret_cast<float*>(H.hi_dst) + ro;
+              if (row0) *reinterpret_cast<float2*>(d) = make_float2(za, zb2);
+              if (row1) *reinterpret_cast<float2*>(d + M.pitch) = make_float2(zc2, zd);
+            }
+          }
         } else {
           // r_P = d u_P
           if (row0) {
@@ -585,6 +614,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
       cu += pplane;
     }
     seq += nplanes;
+    if (push && (zb == 0 || zb + len == D.nz)) halo_signal(H, zb == 0, zb + len == D.nz);
   }
   if (OUT == 2) {
     block_sum<3>(acc, red);
@@ -614,16 +644,21 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ r, co
                                                       const uint8_t* __restrict__ code, const float* __restrict__ gtab,
                                                       float* __restrict__ u, int pitch, const Dom D,
                                                       const Scal* __restrict__ S, int par,
-                                                      double* __restrict__ partials) {
+                                                      double* __restrict__ partials, const HaloPush H) {
   __shared__ double red[32 * 2];
   __shared__ float tab[27 * 128];  // 1 / d
-  if (S->done) return;
+  const bool push = H.lo_dst || H.hi_dst;
+  if (S->done) {
+    if (push) halo_signal(H, 1, 1);
+    return;
+  }
   for (int e = threadIdx.x; e < MG_TAB; e += blockDim.x) tab[e] = gtab[e];
   __syncthreads();
   const double alpha = UPDATE ? S->rz[par] / S->pq : 0.0;
   const long rows = (long)D.ny * D.nz;
   double acc[2] = {0, 0};
-  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+  // one row (y, z); `remote`: the same row of a neighbour's halo plane (slab-boundary planes only)
+  auto do_row = [&](long row, float* remote) {
     const int y = (int)(row % D.ny), z = (int)(row / D.ny);
     const float* trow = tab + ((3 * mg_cls(y, D.ny) + 9 * mg_cls(D.z0 + z, D.nzg)) << 7);
     const long base = row * D.nx;
@@ -640,9 +675,23 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ r, co
       }
       const unsigned cc = *reinterpret_cast<const unsigned short*>(code + i);
       const float t0 = trow[(mg_cls(xx, D.nx) << 7) | (cc & 127u)], t1 = trow[(mg_cls(xx + 1, D.nx) << 7) | ((cc >> 8) & 127u)];
-      *reinterpret_cast<float2*>(urow + xx) = make_float2((float)vr.x * t0, (float)vr.y * t1);
+      const float2 uv = make_float2((float)vr.x * t0, (float)vr.y * t1);
+      *reinterpret_cast<float2*>(urow + xx) = uv;
+      if (remote) *reinterpret_cast<float2*>(remote + xx) = uv;
     }
+  };
+  long first = 0, last = rows;  // rows of the interior planes
+  if (push && D.nz >= 2) {
+    // the two slab-boundary planes first: their u goes into the neighbours' halo planes while the rest is worked on
+    first = D.ny;
+    last = rows - D.ny;
+    for (long y = blockIdx.x; y < D.ny; y += gridDim.x) {
+      do_row(y, H.lo_dst ? reinterpret_cast<float*>(H.lo_dst) + y * pitch : nullptr);
+      do_row(last + y, H.hi_dst ? reinterpret_cast<float*>(H.hi_dst) + y * pitch : nullptr);
+    }
+    halo_signal(H, 1, 1);
   }
+  for (long row = first + blockIdx.x; row < last; row += gridDim.x) do_row(row, nullptr);
   if (UPDATE) {
     block_sum<2>(acc, red);
     if (threadIdx.x == 0) {
@@ -654,12 +703,17 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ r, co
 
 __global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, double* __restrict__ p,
                                                    const float* __restrict__ z, long n2, long n,
-                                                   const Scal* __restrict__ S, int par, long long kit, int first) {
+                                                   const Scal* __restrict__ S, int par, long long kit, int first,
+                                                   const HaloPush H, long plane2) {
   const bool upd_x = !first && S->it == kit + 1, upd_p = !S->done;
-  if (!upd_x && !upd_p) return;
+  const bool push = (H.lo_dst || H.hi_dst) && n2 >= 2 * plane2;
+  if (!upd_x && !upd_p) {
+    if (push) halo_signal(H, 1, 1);
+    return;
+  }
   const double alpha = upd_x ? S->rz[par] / S->pq : 0.0;
   const double beta = first ? 0.0 : S->rz[par ^ 1] / S->rz[par];
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
+  auto body = [&](long i, double2* remote) {
     double2 vp = reinterpret_cast<double2*>(p)[i];
     if (upd_x) {
       double2 vx = reinterpret_cast<double2*>(x)[i];
@@ -672,8 +726,23 @@ __global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, doubl
       vp.x = (double)vz.x + beta * vp.x;
       vp.y = (double)vz.y + beta * vp.y;
       reinterpret_cast<double2*>(p)[i] = vp;
+      if (remote) *remote = vp;
     }
+  };
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  long lo = 0, hi = n2;  // the interior planes
+  if (push) {
+    // the two slab-boundary planes first: the new p goes into the neighbours' halo planes (NVLink stores) while
+    // the interior is still being updated
+    lo = plane2;
+    hi = n2 - plane2;
+    for (long i = g; i < plane2; i += stride) {
+      body(i, H.lo_dst ? reinterpret_cast<double2*>(H.lo_dst) + i : nullptr);
+      body(hi + i, H.hi_dst ? reinterpret_cast<double2*>(H.hi_dst) + i : nullptr);
+    }
+    halo_signal(H, 1, 1);
   }
+  for (long i = lo + g; i < hi; i += stride) body(i, nullptr);
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     if (upd_x) x[n - 1] += alpha * p[n - 1];
     if (upd_p) p[n - 1] = (double)z[n - 1] + beta * p[n - 1];

@@ -309,12 +309,14 @@ inline int link_publish(Ctx& c, const Dom& D, bool reset) {
 
 // Push the boundary planes of a plane-major array that lives in window `win` of my workspace into my
 // neighbours' halo planes (plane0 = my plane 0; halo planes at -1 and nz), and wait for theirs.
-inline int link_exchange(Ctx& c, int field, int win, char* plane0, size_t plane_bytes, int nz) {
+// fine_grid: the array has as many planes as the slab (x, p: the lower neighbour's slab may be one plane longer or
+// shorter); every other array belongs to the multigrid path, which requires equal slabs.
+inline int link_exchange(Ctx& c, int field, int win, char* plane0, size_t plane_bytes, int nz, bool fine_grid = false) {
   Link& L = c.link;
   Mail* mine = L.mail[L.rank];
   const size_t off = (size_t)(plane0 - link_my_base(c, win));
   const bool lo = L.rank > 0, hi = L.rank < L.world - 1;
-  char* lo_dst = lo ? L.nb[0][win] + off + (size_t)L.nb_nz[0] * plane_bytes : nullptr;
+  char* lo_dst = lo ? L.nb[0][win] + off + (size_t)(fine_grid ? L.nb_nz[0] : nz) * plane_bytes : nullptr;
   char* hi_dst = hi ? L.nb[1][win] + off - plane_bytes : nullptr;
   if ((lo && !L.nb[0][win]) || (hi && !L.nb[1][win])) return fail(KEFFB200_ESTATE, "neighbour window %d is not mapped", win);
   const int g = push_ctas(plane_bytes);

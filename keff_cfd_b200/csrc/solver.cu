@@ -158,7 +158,7 @@ static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
   const size_t plane = (size_t)D.nx * D.ny;
   if (c.link.p2p) {
     const bool is_x = f_halo == c.x;
-    return link_exchange(c, is_x ? HF_X : HF_P, is_x ? W_X : W_P, (char*)(f_halo + plane), plane * 8, D.nz);
+    return link_exchange(c, is_x ? HF_X : HF_P, is_x ? W_X : W_P, (char*)(f_halo + plane), plane * 8, D.nz, true);
   }
   if (n.world <= 1 || !n.comm) return 0;
   double* lo_halo = f_halo;
@@ -207,6 +207,47 @@ static int allgather_f32(const float* src, float* dst, size_t count) {
   if (c.link.p2p) return link_gather(c, (const char*)src, count * sizeof(float));
   Nccl& n = c.nccl;
   return nccl_check(n.AllGather(src, dst, count, /*ncclFloat32*/ 7, n.comm, c.st), "ncclAllGather");
+}
+
+// ---- halo planes pushed by the producing kernel itself -------------------------------------------------
+// The producers of p, u and the two iterate fields of the voxel grid (20 of the 22 MB a rank sends per iteration at
+// 1024^2 planes) store their slab-boundary planes into the neighbours' halo planes themselves, first thing, and the
+// transfer rides under the rest of the kernel; the consumer side is a one-thread wait on the arrival counter.
+// All these arrays are halo'ed buffers that start at their window's base: plane -1 at offset 0, plane nz at nz + 1.
+struct Fused {
+  bool on = false;
+  int field = 0;
+  HaloPush H{nullptr, nullptr, nullptr, nullptr};
+};
+static Fused fused_push(int field, int win, size_t plane_bytes, int nz) {
+  Ctx& c = ctx();
+  Fused f;
+  f.field = field;
+  static const bool off = getenv("KEFFB200_SLAB_NOFUSE") != nullptr;  // experiments: separate push kernels
+  if (!c.dist_active || !c.link.p2p || nz < 2 || off) return f;
+  Link& L = c.link;
+  const bool lo = L.rank > 0, hi = L.rank < L.world - 1;
+  if ((lo && !L.nb[0][win]) || (hi && !L.nb[1][win])) return f;
+  f.on = true;
+  f.H.lo_dst = lo ? L.nb[0][win] + (size_t)(nz + 1) * plane_bytes : nullptr;
+  f.H.hi_dst = hi ? L.nb[1][win] : nullptr;
+  f.H.lo_flag = lo ? &L.mail[L.rank - 1]->halo[field][1] : nullptr;
+  f.H.hi_flag = hi ? &L.mail[L.rank + 1]->halo[field][0] : nullptr;
+  return f;
+}
+// after the producer's launch: `units` arrivals per side are on their way into my halos as well
+static int fused_wait(const Fused& f, unsigned units) {
+  if (!f.on) return 0;
+  Ctx& c = ctx();
+  Link& L = c.link;
+  Mail* mine = L.mail[L.rank];
+  const bool lo = L.rank > 0, hi = L.rank < L.world - 1;
+  if (lo) L.expect[f.field][0] += units;
+  if (hi) L.expect[f.field][1] += units;
+  k_wait_halo<<<1, 32, 0, c.st>>>(lo ? &mine->halo[f.field][0] : nullptr, L.expect[f.field][0], hi ? &mine->halo[f.field][1] : nullptr,
+                                  L.expect[f.field][1], c.S);
+  KB_LAUNCHED();
+  return 0;
 }
 
 // ---- stencil launcher ---------------------------------------------------------------------------
@@ -287,6 +328,7 @@ static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
     }
     const int G = c.sms * occ;
     Plan pl;
+    pl.bfirst = 0;
     pl.ntx = (D.nx + TX - 1) / TX;
     pl.nty = (D.ny + TY - 1) / TY;
     const long tiles = (long)pl.ntx * pl.nty;
@@ -359,6 +401,7 @@ struct Mg {
   int grid = 0, gu = 0;        // CTAs of the stencil passes / of the row-wise vector kernels
   int nu = 2;                  // smoothing sweeps before and after the coarse correction
   float om[4] = {0.595f, 1.614f, 0.f, 0.f};  // their weights (Chebyshev points of [0.4, 1.9] for nu = 2)
+  bool u_pushed = false;       // the kernel that wrote u has already delivered its boundary planes to the neighbours
   int nu0 = 2;                 // the same for the voxel grid alone (KEFFB200_MG_OMEGA0 overrides; default = nu, om)
   float om0[4] = {0.595f, 1.614f, 0.f, 0.f};
   Dom D{};
@@ -616,6 +659,7 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
   }
   const int G = c.sms * occ;
   Plan pl;
+  pl.bfirst = mg.dist ? 1 : 0;
   pl.ntx = (D.nx + TX - 1) / TX;
   pl.nty = (D.ny + TY - 1) / TY;
   const long tiles = (long)pl.ntx * pl.nty;
@@ -643,13 +687,15 @@ static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
 }
 
 // u = r / d from a residual that some other kernel produced
-static int mg_make_u(const Mg& mg, double* r) {
+static int mg_make_u(Mg& mg, double* r) {
   Ctx& c = ctx();
   const int vt = vec_threads(mg.D.nx, 2);
+  const Fused f = fused_push(HF_U, W_U, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz);
   k_cg_update_mg<0><<<mg.gu, vt, 0, c.st>>>(r, nullptr, c.code, c.mg_tab, c.u + (size_t)mg.pitch * mg.D.ny, mg.pitch, mg.D,
-                                            c.S, 0, c.partials);
+                                            c.S, 0, c.partials, f.H);
   KB_LAUNCHED();
-  return 0;
+  mg.u_pushed = f.on;
+  return fused_wait(f, (unsigned)mg.gu);
 }
 
 // One pass over the voxel grid.  in: 0 = u, 1/2 = iterate field 0/1;  out: -1 restrict, -2 z, 0/1 iterate field.
@@ -665,8 +711,10 @@ static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass&
   const CUtensorMap& tm = in == 0 ? mg.tm_u : mg.tm_x[in - 1];
   const float* uown = c.u + uplane;
   float* fout = out >= 0 ? c.xf[out] + uplane : nullptr;
+  Fused f;
+  if (out >= 0) f = fused_push(out == 0 ? HF_XF0 : HF_XF1, out == 0 ? W_XF0 : W_XF1, uplane * sizeof(float), mg.D.nz);
 #define KB_FINE(O, E, U) \
-  k_mg_fine<O, E, U><<<mg.grid, NTHR, 0, c.st>>>(tm, c.code, c.mg_tab, uown, fout, z, mf, K, mg.C, mg.D, mg.plan, c.S, c.partials)
+  k_mg_fine<O, E, U><<<mg.grid, NTHR, 0, c.st>>>(tm, c.code, c.mg_tab, uown, fout, z, mf, K, mg.C, mg.D, mg.plan, c.S, c.partials, f.H)
   const bool isu = in == 0;
   if (out == -1) {
     if (isu) KB_FINE(0, 0, 1); else KB_FINE(0, 0, 0);
@@ -680,9 +728,11 @@ static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass&
   }
 #undef KB_FINE
   KB_LAUNCHED();
-  if (out >= 0)
+  if (out >= 0) {
+    if (f.on) return fused_wait(f, (unsigned)(mg.plan.ntx * mg.plan.nty));  // one arrival per tile of a boundary chunk
     KB_TRY(exchange_planes(out == 0 ? HF_XF0 : HF_XF1, out == 0 ? W_XF0 : W_XF1, c.xf[out] + uplane, uplane * sizeof(float), mg.D.nz,
                            c.st));
+  }
   return 0;
 }
 
@@ -695,7 +745,8 @@ static int mg_vcycle(const Mg& mg, float* z) {
   const int lo = mg.lo, hi = mg.hi, nu = mg.nu, nu0 = mg.nu0;
   const float* w = mg.om;
   const float* w0 = mg.om0;
-  KB_TRY(exchange_planes(HF_U, W_U, c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
+  if (!mg.u_pushed)
+    KB_TRY(exchange_planes(HF_U, W_U, c.u + (size_t)mg.pitch * mg.D.ny, (size_t)mg.pitch * mg.D.ny * sizeof(float), mg.D.nz, c.st));
   // ---- voxel grid, down ----
   int cur = 0;  // field holding the current iterate (0 = u, scaled by w_1)
   float sc = w0[0];
@@ -848,6 +899,7 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   *c.hS = h0;
   KB_CUDA(cudaMemcpyAsync(c.S, c.hS, sizeof(Scal), cudaMemcpyHostToDevice, c.st));
 
+  bool p_pushed = false;  // the kernel that wrote p has already delivered its boundary planes to the neighbours
   // (re)start: r = b - A x, p = z = M r
   auto enqueue_init = [&]() -> int {
     KB_TRY(exchange_halo(c.x, D, c.st));
@@ -858,26 +910,35 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       KB_TRY(mg_make_u(mg, r));
       KB_TRY(mg_vcycle(mg, c.z));
       KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, 0));
-      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1);
+      const Fused f = fused_push(HF_P, W_P, plane * 8, D.nz);
+      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1, f.H, (long)(plane / 2));
       KB_LAUNCHED();
+      p_pushed = f.on;
+      KB_TRY(fused_wait(f, (unsigned)gm));
     }
     return 0;
   };
   // iteration k since the last (re)start; every kernel returns at once when the stop flag is up
   auto enqueue_iter = [&](long k) -> int {
     const int par = (int)(k & 1);
-    KB_TRY(exchange_halo(c.p, D, c.st));
+    if (!p_pushed) KB_TRY(exchange_halo(c.p, D, c.st));
     KB_TRY(stencil_launch<MODE_APPLY>(s, 1, q, nullptr));
     KB_TRY(reduce_step<RS_PQ>(s.grid, 0));
     if (mg.on) {
+      const Fused fu = fused_push(HF_U, W_U, (size_t)mg.pitch * D.ny * sizeof(float), D.nz);
       k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(r, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D, c.S, par,
-                                                c.partials);
+                                                c.partials, fu.H);
       KB_LAUNCHED();
+      mg.u_pushed = fu.on;
       KB_TRY(reduce_step<RS_RR_MG>(mg.gu, 0));
+      KB_TRY(fused_wait(fu, (unsigned)mg.gu));
       KB_TRY(mg_vcycle(mg, c.z));
       KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, par ^ 1));
-      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0);
+      const Fused fp = fused_push(HF_P, W_P, plane * 8, D.nz);
+      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0, fp.H, (long)(plane / 2));
       KB_LAUNCHED();
+      p_pushed = fp.on;
+      KB_TRY(fused_wait(fp, (unsigned)gm));
       return 0;
     }
     if (V == 2) k_cg_update<2><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);

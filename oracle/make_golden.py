@@ -138,7 +138,30 @@ def discrete():
         print(k, v)
 
 
+def discrete_big():
+    """Discrete solutions at the bench's own generators and larger sizes: the splitmix Bernoulli volumes at 128^3
+    and 256^3 (configs[3]/[4] scaled to what a CPU finishes: BASELINE.md 4.5) and 256 of the 10,000 bench images."""
+    from keff_cfd_b200 import structures as S
+    out = {}
+    for n, sub in ((128, 4), (256, 8)):
+        m = S.bernoulli_volume((n, n, n), 0.5, 1234)
+        t0 = time.time()
+        d = refbind.orc_discrete(m)
+        out[f"bernoulli_{n}_seed1234"] = {k: d[k] for k in ("keff", "Q1", "Q2", "iters", "relres")}
+        out[f"bernoulli_{n}_seed1234"]["seconds"] = round(time.time() - t0, 1)
+        np.save(os.path.join(GOLD, f"discrete_bernoulli_{n}_Tsub{sub}.npy"), d["T"][::sub, ::sub, ::sub].copy())
+        print(n, out[f"bernoulli_{n}_seed1234"], flush=True)
+    idx = [39 * i for i in range(256)]
+    keff = []
+    for i in idx:
+        d = refbind.orc_discrete(S.to_gray(S.disc_image(i)))
+        keff.append([i, d["keff"], d["Q1"], d["Q2"], d["relres"]])
+    np.save(os.path.join(GOLD, "discrete_bench_images.npy"), np.array(keff))
+    json.dump(out, open(os.path.join(GOLD, "discrete_big.json"), "w"), indent=1, sort_keys=True)
+    print("bench images:", len(keff), "max relres", max(k[4] for k in keff))
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
-    {"prep": prep, "ref2d": ref2d, "binary2d": binary2d, "discrete": discrete}.get(
+    {"prep": prep, "ref2d": ref2d, "binary2d": binary2d, "discrete": discrete, "discrete_big": discrete_big}.get(
         cmd, lambda: ref3d(*sys.argv[2:4]))()

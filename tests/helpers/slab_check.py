@@ -15,12 +15,12 @@ loc = api.bernoulli_volume_dev((nzl, n, n), 0.5, 1234, z0=z0, device=local)
 halo = D.exchange_structure_halos(loc, rank, world)
 p = api.default_params()
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-r = D.solve3d_slab(halo, z0, nzg, p, want_T=(n <= 128))
+r = D.solve3d_slab(halo, z0, nzg, p, want_T=(n <= 256))
 torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
 if rank == 0:
     print("transport:", "peer-memory" if D.peer_memory() else "nccl")
     print(f"slab {n}x{n}x{nzg} over {world} ranks:", {k: r[k] for k in ("keff", "q_left", "q_right", "rel_residual", "iters", "status", "gpu_ms")}, f"wall {dt:.3f}s")
-if n <= 128:
+if n <= 256:
     parts = [torch.empty_like(r["T"]) for _ in range(world)] if nzg % world == 0 else None
     if parts is not None:
         dist.all_gather(parts, r["T"])
