@@ -24,6 +24,7 @@
 #ifndef KEFFB200_H
 #define KEFFB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -160,6 +161,22 @@ int keffb200_flux(const uint8_t* solid, int nx, int ny, int nz, const keffb200_p
  * the multigrid path does not take (see KEFFB200_F_NO_MG). */
 int keffb200_precond(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* r,
                      double* z);
+/* x-direction heat-flux field of a given host field T: Qx[z][y][j], j = 0..nx, the flux through the face between
+ * cells j-1 and j (j = 0 and j = nx: the fixed-temperature walls), the quantity behind printQMAP
+ * (Keff2D/keff2D.h:427-479: harmonic-mean face fluxes; the reference prints "not currently available" in 3D,
+ * Keff3D/keff3D.cpp:179-181).  Qx holds nz*ny*(nx+1) doubles. */
+int keffb200_flux_field(const uint8_t* solid, int nx, int ny, int nz, const keffb200_params* p, const double* T,
+                        double* Qx);
+/* Warm start for the mesh-convergence mode: (tri)linear interpolation of a field from an sx*sy*sz mesh of the unit
+ * cube onto an nx*ny*nz mesh, with the fixed-temperature walls as interpolation nodes along x.  Replaces
+ * SolExpandSimple (Keff2D/keff2D.h:614-642), which replicates values without interpolating.  Host buffers. */
+int keffb200_interpolate(const double* T_src, int sx, int sy, int sz, double* T_dst, int nx, int ny, int nz,
+                         double tl, double tr);
+/* Page-locked host memory for the buffers handed to the host-buffer entry points (optional: pageable memory works,
+ * but its copies are staged by the driver and do not overlap with the solves). */
+void* keffb200_host_alloc(size_t bytes);
+void keffb200_host_free(void* p);
+
 /* Timing hook: `reps` applications of the stencil kernel on device-resident data
  * (one cell-update per cell per application, 16 B/cell of compulsory traffic).  Returns the average
  * milliseconds per application, measured with CUDA events on the launching stream. */

@@ -42,7 +42,8 @@ EXPORTS = [
     "keffb200_dist_init", "keffb200_dist_shutdown", "keffb200_solve3d_slab_dev", "keffb200_apply",
     "keffb200_flux", "keffb200_bench_apply_dev", "keffb200_gen_bernoulli_dev", "keffb200_precond",
     "keffb200_timer_start", "keffb200_timer_stop", "keffb200_init_multi", "keffb200_device_count",
-    "keffb200_set_slab_min_cells", "keffb200_dist_peer_memory", "keffb200_wait_stream",
+    "keffb200_set_slab_min_cells", "keffb200_dist_peer_memory", "keffb200_wait_stream", "keffb200_flux_field",
+    "keffb200_interpolate", "keffb200_host_alloc", "keffb200_host_free",
 ]
 
 _lib = None
@@ -71,6 +72,12 @@ def lib():
         L.keffb200_set_slab_min_cells.argtypes = [C.c_long]
         L.keffb200_set_slab_min_cells.restype = None
         L.keffb200_wait_stream.argtypes = [C.c_void_p]
+        L.keffb200_flux_field.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, dp]
+        L.keffb200_interpolate.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.keffb200_host_alloc.argtypes = [C.c_size_t]
+        L.keffb200_host_alloc.restype = C.c_void_p
+        L.keffb200_host_free.argtypes = [C.c_void_p]
+        L.keffb200_host_free.restype = None
         L.keffb200_default_params.argtypes = [PP]
         L.keffb200_solve2d.argtypes = [u8p, C.c_int, C.c_int, PP, dp, dp, dp, dp, RP]
         L.keffb200_solve2d_batch.argtypes = [u8p, C.c_int, C.c_int, C.c_int, PP, dp, RP]

@@ -226,6 +226,33 @@ def boundary_flux(solid, T, params=None, device=None):
     return _res(r, qL=qL, qR=qR)
 
 
+def flux_field(solid, T, params=None, device=None):
+    """x-direction heat-flux field behind the Q-maps: Qx[z, y, 0..nx] (printQMAP, Keff2D/keff2D.h:427-479)."""
+    device = _lib.ensure(device)
+    p = params or default_params()
+    solid = np.ascontiguousarray(solid, dtype=np.uint8)
+    squeeze = solid.ndim == 2
+    if squeeze:
+        solid = solid[None]
+    nz, ny, nx = solid.shape
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(nz, ny, nx)
+    Q = np.empty((nz, ny, nx + 1))
+    check(lib().keffb200_flux_field(_addr(solid), nx, ny, nz, C.byref(p), _addr(T), _addr(Q)))
+    return Q[0] if squeeze else Q
+
+
+def interpolate(T, shape, tl=0.0, tr=1.0, device=None):
+    """Warm start for a finer mesh: (tri)linear interpolation of T onto `shape`, walls as nodes along x."""
+    device = _lib.ensure(device)
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    src = T if T.ndim == 3 else T[None]
+    dst_shape = tuple(shape) if len(shape) == 3 else (1,) + tuple(shape)
+    out = np.empty(dst_shape)
+    check(lib().keffb200_interpolate(_addr(src), src.shape[2], src.shape[1], src.shape[0], _addr(out), dst_shape[2], dst_shape[1],
+                                     dst_shape[0], tl, tr))
+    return out.reshape(shape)
+
+
 def bench_apply(solid_dev, params=None, reps=20, device=None):
     """Average ms per stencil application on a device-resident structure (CUDA events)."""
     device = _lib.ensure(device, solid_dev)

@@ -164,6 +164,10 @@ inline void debug_sync(const char* file, int line) {
 
 #define KB_LAUNCHED() (kb::ctx().launches++, kb::debug_sync(__FILE__, __LINE__))
 
+// solver.cu
+keffb200_params norm_params(const keffb200_params* p);
+Coef make_coef(int nx, int ny, int nzg, const keffb200_params& P);
+
 constexpr int PARTIAL_SLOTS = 1 << 15;  // per-CTA partial sums, 3 doubles each
 
 }  // namespace kb

@@ -109,16 +109,18 @@ inline bool structure_from_csv(const std::string& path, int W, int H, int D, std
 }
 
 // createOutput rows.  2D: Keff2D/keff2D.h:245-246; 3D: Keff3D/keff3D.h:308-309 (adds MeshIncreaseZ).
+// nElements is an int in the reference (it overflows beyond 2^31 cells); here it is printed from a long, which gives
+// the same text wherever the reference's is right.
 inline bool append_row(const Options& o, bool three_d, double keff, double Q1, double Q2, long iters, const char* input,
-                       int nElements, double porosity, double seconds, int nCores) {
+                       long nElements, double porosity, double seconds, int nCores) {
   FILE* f = fopen(o.outputFilename.c_str(), "a+");
   if (!f) return false;
   if (three_d)
-    fprintf(f, "%.10lf,%f,%f,%ld,%.10lf,%s,%d,%d,%d,%d,%f,%f,%f,%f,%f,%f,%d\n", keff, Q1, Q2, iters, o.ConvergeCriteria,
+    fprintf(f, "%.10lf,%f,%f,%ld,%.10lf,%s,%ld,%d,%d,%d,%f,%f,%f,%f,%f,%f,%d\n", keff, Q1, Q2, iters, o.ConvergeCriteria,
             input, nElements, o.MeshIncreaseX, o.MeshIncreaseY, o.MeshIncreaseZ, porosity, o.TCsolid, o.TCfluid,
             o.TempLeft, o.TempRight, seconds, nCores);
   else
-    fprintf(f, "%.10lf,%f,%f,%ld,%.10lf,%s,%d,%d,%d,%f,%f,%f,%f,%f,%f,%d\n", keff, Q1, Q2, iters, o.ConvergeCriteria, input,
+    fprintf(f, "%.10lf,%f,%f,%ld,%.10lf,%s,%ld,%d,%d,%f,%f,%f,%f,%f,%f,%d\n", keff, Q1, Q2, iters, o.ConvergeCriteria, input,
             nElements, o.MeshIncreaseX, o.MeshIncreaseY, porosity, o.TCsolid, o.TCfluid, o.TempLeft, o.TempRight, seconds,
             nCores);
   fclose(f);
@@ -141,27 +143,34 @@ inline bool write_tmap(const std::string& name, const double* T, int nx, int ny,
   return true;
 }
 
-// printQMAP (keff2D.h:427-479): x-direction face fluxes, nx+1 values per row: the wall fluxes at
-// j = 0 and j = nx, harmonic-mean face fluxes in between.
-inline bool write_qmap2d(const std::string& name, const double* T, const uint8_t* solid, int nx, int ny, double ks,
-                         double kf, const double* qL, const double* qR) {
+// printQMAP (keff2D.h:427-479): x-direction face fluxes, nx+1 values per row: the wall fluxes at j = 0 and j = nx,
+// harmonic-mean face fluxes in between -- evaluated on the GPU (keffb200_flux_field); 2D "x,y,Q", and the 3D map the
+// reference announces but never wrote (keff3D.cpp:179-181) as "x,y,z,Q".
+inline bool write_qmap(const std::string& name, const double* Qx, int nx, int ny, int nz, bool three_d) {
   FILE* f = fopen(name.c_str(), "w+");
   if (!f) return false;
-  fprintf(f, "x,y,Q\n");
-  const double dx = 1.0 / nx, dy = 1.0 / ny;
-  for (int i = 0; i < ny; i++)
-    for (int j = 0; j <= nx; j++) {
-      double q;
-      if (j == 0) q = qL[i];
-      else if (j == nx) q = qR[i];
-      else {
-        const double ka = solid[(size_t)i * nx + j] ? ks : kf, kb = solid[(size_t)i * nx + j - 1] ? ks : kf;
-        q = dy / dx * (2.0 * ka * kb / (ka + kb)) * (T[(size_t)i * nx + j] - T[(size_t)i * nx + j - 1]);
+  fprintf(f, three_d ? "x,y,z,Q\n" : "x,y,Q\n");
+  for (int k = 0; k < nz; k++)
+    for (int i = 0; i < ny; i++)
+      for (int j = 0; j <= nx; j++) {
+        const double q = Qx[((size_t)k * ny + i) * (nx + 1) + j];
+        if (three_d) fprintf(f, "%d,%d,%d,%f\n", j, i, k, q);
+        else fprintf(f, "%d,%d,%f\n", j, i, q);
       }
-      fprintf(f, "%d,%d,%f\n", j, i, q);
-    }
   fclose(f);
   return true;
+}
+
+// 3D structure replicated by an integer factor per direction (the mesh-convergence mode, Keff3D/keff3D.cpp:226-243)
+inline void amplify3d(const std::vector<uint8_t>& s, int W, int H, int D, int ax, int ay, int az, std::vector<uint8_t>& out) {
+  const int nx = W * ax, ny = H * ay, nz = D * az;
+  out.resize((size_t)nx * ny * nz);
+  for (int k = 0; k < nz; k++)
+    for (int j = 0; j < ny; j++) {
+      const uint8_t* src = s.data() + ((size_t)(k / az) * H + j / ay) * W;
+      uint8_t* dst = out.data() + ((size_t)k * ny + j) * nx;
+      for (int i = 0; i < nx; i++) dst[i] = src[i / ax];
+    }
 }
 
 inline int die(const char* what) {

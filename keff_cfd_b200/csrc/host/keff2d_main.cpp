@@ -40,12 +40,22 @@ int main(int argc, char** argv) {
     if (!load_jpeg_gray("00000.jpg", first)) { fprintf(stderr, "keff2D: 00000.jpg: %s\n", first.err.c_str()); return 1; }
     const int nx = first.w * o.MeshIncreaseX, ny = first.h * o.MeshIncreaseY;
     const size_t cells = (size_t)nx * ny;
-    std::vector<uint8_t> all(cells * o.NumImg);
+    // every visible GPU takes a share of each chunk (keffb200_init_multi); the staging array is page-locked so the
+    // copies to the GPUs run at PCIe rate underneath the solves
+    int n_gpus = 1;
+    if (!check_only) {
+      if (keffb200_init_multi(0)) return die("init");
+      n_gpus = std::max(1, keffb200_device_count());
+    }
+    uint8_t* all = check_only ? (uint8_t*)malloc(cells * o.NumImg) : (uint8_t*)keffb200_host_alloc(cells * o.NumImg);
+    const bool pinned = !check_only && all != nullptr;
+    if (!all) all = (uint8_t*)malloc(cells * o.NumImg);
+    if (!all) { fprintf(stderr, "keff2D: cannot allocate the image staging array\n"); return 1; }
     std::vector<double> poro(o.NumImg);
     std::vector<keffb200_result> res(o.NumImg);
     std::vector<double> T;
-    if (o.printTmap && !check_only) T.resize(all.size());
-    const int chunk = std::max(1, std::min(o.NumImg, 2048));
+    if (o.printTmap && !check_only) T.resize(cells * o.NumImg);
+    const int chunk = std::max(1, std::min(o.NumImg, 2048 * n_gpus));
     const int nchunks = (o.NumImg + chunk - 1) / chunk;
     std::vector<std::atomic<int>> left(nchunks);  // images of the chunk still being decoded
     for (int k = 0; k < nchunks; k++) left[k] = std::min(chunk, o.NumImg - k * chunk);
@@ -72,7 +82,7 @@ int main(int argc, char** argv) {
         if (g.channels != 1) fprintf(stderr, "keff2D: warning: %s has %d channels, using luminance\n", name, g.channels);
         std::vector<uint8_t> sl;
         structure_from_image(g, o.MeshIncreaseX, o.MeshIncreaseY, sl, poro[img]);
-        memcpy(all.data() + cells * img, sl.data(), cells);
+        memcpy(all + cells * img, sl.data(), cells);
         if (--left[img / chunk] == 0) {
           std::lock_guard<std::mutex> lk(mu);
           cv.notify_all();
@@ -83,7 +93,6 @@ int main(int argc, char** argv) {
     std::vector<std::thread> pool;
     for (int t = 0; t < nthreads; t++) pool.emplace_back(decode);
     int rc = 0;
-    if (!check_only && keffb200_init(0)) rc = die("init");
     for (int k = 0; k < nchunks && rc == 0; k++) {
       {
         std::unique_lock<std::mutex> lk(mu);
@@ -92,7 +101,7 @@ int main(int argc, char** argv) {
       if (failed) break;
       if (check_only) continue;
       const int i0 = k * chunk, cnt = std::min(chunk, o.NumImg - i0);
-      if (keffb200_solve2d_batch(all.data() + cells * i0, cnt, nx, ny, &p, o.printTmap ? T.data() + cells * i0 : nullptr,
+      if (keffb200_solve2d_batch(all + cells * i0, cnt, nx, ny, &p, o.printTmap ? T.data() + cells * i0 : nullptr,
                                  res.data() + i0))
         rc = die("solve2d_batch");
     }
@@ -105,13 +114,17 @@ int main(int argc, char** argv) {
     for (int img = 0; img < o.NumImg; img++) {
       char name[64];
       snprintf(name, sizeof name, "%05d.csv", img);  // the reference names batch rows %05d.csv (keff2D.h:271)
-      append_row(o, false, res[img].keff, res[img].q_left, res[img].q_right, res[img].iters, name, nx * ny, poro[img], per, 1);
+      append_row(o, false, res[img].keff, res[img].q_left, res[img].q_right, res[img].iters, name, (long)nx * ny, poro[img], per, 1);
       if (o.printTmap) {
         snprintf(name, sizeof name, "TMAP_%05d.csv", img);
         write_tmap(name, T.data() + cells * img, nx, ny, 1, false);
       }
     }
-    if (o.verbose) printf("Done, saving output (%d images, %d decode threads, %.3f s)\n", o.NumImg, nthreads, since(t0));
+    if (o.verbose)
+      printf("Done, saving output (%d images, %d decode threads, %d GPU%s, %.3f s)\n", o.NumImg, nthreads, n_gpus, n_gpus > 1 ? "s" : "",
+             since(t0));
+    if (pinned) keffb200_host_free(all);
+    else free(all);
     keffb200_shutdown();
     return 0;
   }
@@ -144,20 +157,26 @@ int main(int argc, char** argv) {
     structure_from_image(g, ax, ay, solid, porosity);
     const int nx = g.w * ax, ny = g.h * ay;
     std::vector<double> T((size_t)nx * ny), qL(ny), qR(ny), Tinit;
-    if (!Tprev.empty()) {  // warm start: replicate the previous mesh's field (SolExpandSimple, keff2D.h:614-642)
+    if (!Tprev.empty()) {
+      // warm start from the previous mesh.  The reference replicates the native-mesh field (SolExpandSimple,
+      // keff2D.h:614-642) -- and then overwrites it (keff2D.cpp:268); here the previous field is interpolated
+      // bilinearly, with the two walls as nodes, so each refinement starts within discretisation error of its answer.
       Tinit.resize(T.size());
-      for (int r = 0; r < ny; r++)
-        for (int c = 0; c < nx; c++) Tinit[(size_t)r * nx + c] = Tprev[(size_t)(r * pny / ny) * pnx + c * pnx / nx];
+      if (keffb200_interpolate(Tprev.data(), pnx, pny, 1, Tinit.data(), nx, ny, 1, o.TempLeft, o.TempRight)) return die("interpolate");
     }
     keffb200_result res;
     if (keffb200_solve2d(solid.data(), nx, ny, &p, Tinit.empty() ? nullptr : Tinit.data(), T.data(), qL.data(), qR.data(), &res))
       return die("solve2d");
     printf("Keff = %f, Total Iterations = %ld\n", res.keff, res.iters);
     if (o.printTmap == 1 && o.MeshFlag == 0) write_tmap(o.TMapName, T.data(), nx, ny, 1, false);
-    if (o.printQmap == 1 && o.MeshFlag == 0) write_qmap2d(o.QMapName, T.data(), solid.data(), nx, ny, o.TCsolid, o.TCfluid, qL.data(), qR.data());
+    if (o.printQmap == 1 && o.MeshFlag == 0) {
+      std::vector<double> Q((size_t)ny * (nx + 1));
+      if (keffb200_flux_field(solid.data(), nx, ny, 1, &p, T.data(), Q.data())) return die("flux_field");
+      write_qmap(o.QMapName, Q.data(), nx, ny, 1, false);
+    }
     const double secs = since(t0);
     printf("Residual = %f\n", res.energy_residual);
-    append_row(o, false, res.keff, res.q_left, res.q_right, res.iters, o.inputFilename.c_str(), nx * ny, porosity, secs, o.numCores);
+    append_row(o, false, res.keff, res.q_left, res.q_right, res.iters, o.inputFilename.c_str(), (long)nx * ny, porosity, secs, o.numCores);
     printf("Time spent = %lf\n", secs);
     if (res.status != 0) fprintf(stderr, "keff2D: warning: stopped at MaxIter before convergence\n");
     Tprev.swap(T);

@@ -20,7 +20,7 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
 int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int nx, int ny, const keffb200_params& P,
                        double* d_T_out, keffb200_result* out);
 
-static keffb200_params norm_params(const keffb200_params* p) {
+keffb200_params norm_params(const keffb200_params* p) {
   keffb200_params P;
   if (p) P = *p; else keffb200_default_params(&P);
   if (P.check_every <= 0) P.check_every = 32;

@@ -112,6 +112,49 @@ def test_schwarz_structures_match_tight_reference(K, name):
         assert rel(t["keff"], r["keff"]) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["schwarz163", "schwarz091"])
+def test_schwarz_full_temperature_field_against_live_oracle(K, R, name):
+    """Every one of the 128^3 temperatures (not a sub-lattice) against the discrete solution of the reference's own
+    assembled system, computed here by the checker (PCG to 1e-12, about half a minute)."""
+    m = schwarz(name)
+    d = R.orc_discrete(m)
+    assert d["relres"] < 1e-11
+    r = K.solve3d(m)
+    assert r["status"] == 0 and rel(r["keff"], d["keff"]) < KEFF_RTOL
+    assert np.abs(r["T"] - d["T"]).max() < T_ATOL
+
+
+@pytest.mark.parametrize("n,sub", [(128, 4), (256, 8)])
+def test_bench_generator_volumes_match_oracle_goldens(K, n, sub):
+    """configs[3]/[4]'s generator (splitmix Bernoulli 0.5, seed 1234) at the sizes a CPU oracle finishes
+    (BASELINE.md 4.5): discrete solutions from oracle/make_golden.py discrete_big."""
+    from keff_cfd_b200 import structures as S
+    d = gold_json("discrete_big.json")[f"bernoulli_{n}_seed1234"]
+    m = S.bernoulli_volume((n, n, n), 0.5, 1234)
+    r = K.solve3d(m)
+    assert r["status"] == 0 and r["iters"] <= 12 and rel(r["keff"], d["keff"]) < KEFF_RTOL
+    assert rel(r["q_left"], d["Q1"]) < KEFF_RTOL and rel(r["q_right"], d["Q2"]) < KEFF_RTOL
+    assert np.abs(r["T"][::sub, ::sub, ::sub] - gold_npy(f"discrete_bernoulli_{n}_Tsub{sub}.npy")).max() < T_ATOL
+
+
+def test_bench_images_match_oracle_goldens(K):
+    """256 of the 10,000 bench images (every 39th, same generator and seeds as bench.py) against their discrete
+    solutions: the batch kernel at the bench's own launch configuration, Keff within 1e-5."""
+    from keff_cfd_b200 import structures as S
+    g = gold_npy("discrete_bench_images.npy")
+    idx = g[:, 0].astype(int)
+    imgs = np.stack([S.disc_image(int(i)) for i in idx])
+    res = K.solve2d_batch(imgs)
+    assert (res["status"] == 0).all()
+    assert (np.abs(res["keff"] - g[:, 1]) <= KEFF_RTOL * g[:, 1]).all(), np.abs(res["keff"] / g[:, 1] - 1).max()
+    assert (np.abs(res["q_left"] - g[:, 2]) <= KEFF_RTOL * g[:, 2]).all()
+    assert (np.abs(res["q_right"] - g[:, 3]) <= KEFF_RTOL * g[:, 3]).all()
+    # the same images inside the full 10,000-image launch (other CTAs, other neighbours in the work queue)
+    if os.environ.get("KEFFB200_SKIP_FULL_BATCH") is None:
+        full = K.solve2d_batch(S.disc_images(10000, 128))
+        assert np.array_equal(full["keff"][idx], res["keff"])
+
+
 @pytest.mark.parametrize("n", [32, 64])
 def test_bernoulli_volumes_match_oracle(K, n):
     from keff_cfd_b200 import structures as S
@@ -330,3 +373,71 @@ def test_batch_kernels_against_direct_solves_at_high_contrast(K):
         j = K.solve2d(imgs[i], K.default_params(flags=K.F_NO_MG, **p), want_T=False)
         assert g["status"] == 0 and abs(g["keff"] - want[i]) <= 2e-6 * want[i]
         assert j["status"] == 0 and abs(j["keff"] - want[i]) <= 1e-5 * want[i]
+
+
+# ------------------------------------------------------------------------------ fields either side of the solve (8f N3, N4)
+def _interp_ref(T, shape, tl, tr):
+    """numpy restatement of keffb200_interpolate: linear in each direction between cell centres, the two x walls
+    as nodes, zero gradient beyond the first / last centre in y and z."""
+    T = T if T.ndim == 3 else T[None]
+    sz, sy, sx = T.shape
+    nz, ny, nx = shape if len(shape) == 3 else (1,) + tuple(shape)
+
+    def axis(n, s):
+        t = (np.arange(n) + 0.5) * s / n - 0.5
+        i0 = np.floor(t).astype(int)
+        w = t - i0
+        i1 = i0 + 1
+        lo = i0 < 0
+        i0 = np.where(lo, 0, i0)
+        i1 = np.where(lo, 0, i1)
+        w = np.where(lo, 0.0, w)
+        i1 = np.minimum(i1, s - 1)
+        i0 = np.minimum(i0, s - 1)
+        return i0, i1, w
+    xs = np.concatenate([[0.0], (np.arange(sx) + 0.5) / sx, [1.0]])
+    xf = (np.arange(nx) + 0.5) / nx
+    rows = np.empty((sz, sy, nx))
+    for z in range(sz):
+        for y in range(sy):
+            rows[z, y] = np.interp(xf, xs, np.concatenate([[tl], T[z, y], [tr]]))
+    y0, y1, wy = axis(ny, sy)
+    z0, z1, wz = axis(nz, sz)
+    a = rows[:, y0] * (1 - wy)[None, :, None] + rows[:, y1] * wy[None, :, None]
+    return a[z0] * (1 - wz)[:, None, None] + a[z1] * wz[:, None, None]
+
+
+@pytest.mark.parametrize("src,dst", [((1, 8, 10), (1, 16, 20)), ((1, 7, 6), (1, 21, 18)), ((4, 5, 6), (8, 10, 12)),
+                                     ((3, 4, 6), (9, 12, 18)), ((2, 3, 4), (2, 3, 4))])
+def test_interpolation_matches_its_restatement(K, src, dst):
+    rng = np.random.default_rng(5)
+    T = rng.random(src)
+    got = K.interpolate(T if src[0] > 1 else T[0], dst if src[0] > 1 else dst[1:], tl=-0.5, tr=2.0)
+    want = _interp_ref(T, dst, -0.5, 2.0)
+    assert np.abs(got.reshape(dst) - want).max() < 1e-13
+    # a field that is linear between the walls is reproduced exactly on any mesh
+    lin = np.broadcast_to(-0.5 + 2.5 * (np.arange(src[2]) + 0.5) / src[2], src).copy()
+    out = K.interpolate(lin, dst, tl=-0.5, tr=2.0)
+    assert np.abs(out - (-0.5 + 2.5 * (np.arange(dst[2]) + 0.5) / dst[2])).max() < 1e-13
+
+
+def test_flux_field_matches_the_reference_formula(K):
+    """Qx against printQMAP's expressions (Keff2D/keff2D.h:427-479), 2D and 3D; at a converged field the flux through
+    every plane of faces x = const is the same (energy conservation) and equals Keff * (TR - TL)."""
+    from keff_cfd_b200 import structures as S
+    for m in (S.disc_image(7, n=48), S.bernoulli_volume((10, 12, 16), 0.4, 8)):
+        vol = m if m.ndim == 3 else m[None]
+        nz, ny, nx = vol.shape
+        p = K.default_params(ks=6.0, kf=0.5, tl=0.2, tr=1.7, rel_residual=1e-11)
+        r = K.solve3d(vol, p)
+        Q = K.flux_field(vol, r["T"], p)
+        k = np.where(vol == 1, 6.0, 0.5)
+        dx, dy, dz = 1.0 / nx, 1.0 / ny, (1.0 / nz if nz > 1 else 1.0)
+        want = np.empty((nz, ny, nx + 1))
+        want[..., 0] = k[..., 0] * dy * dz / (dx / 2) * (r["T"][..., 0] - 0.2)
+        want[..., nx] = k[..., -1] * dy * dz / (dx / 2) * (1.7 - r["T"][..., -1])
+        hm = 2 * k[..., 1:] * k[..., :-1] / (k[..., 1:] + k[..., :-1])
+        want[..., 1:nx] = hm * dy * dz / dx * (r["T"][..., 1:] - r["T"][..., :-1])
+        assert np.abs(Q - want).max() < 1e-12 * np.abs(want).max()
+        per_plane = Q.sum(axis=(0, 1))
+        assert np.abs(per_plane - r["keff"] * 1.5).max() < 1e-7 * abs(r["keff"])

@@ -162,3 +162,72 @@ def test_batch_decode_pipeline_on_cpu(built, tmp_path):
     os.remove(os.path.join(d, "00020.jpg"))
     r = subprocess.run([os.path.join(built, "keff2D"), "input.txt", "--check-inputs"], cwd=d, capture_output=True, text=True)
     assert r.returncode == 1 and "00020.jpg" in r.stderr
+
+
+@pytest.mark.gpu
+def test_mesh_convergence_modes_against_oracle(built, tmp_path, R):
+    """MeshFlag: 1 (Keff2D/keff2D.cpp:193-332, Keff3D/keff3D.cpp:187-331): one row per mesh m = 1..MaxMesh, each
+    against the discrete solution of the m-times amplified structure; warm-started meshes take fewer iterations."""
+    from PIL import Image
+    from keff_cfd_b200 import structures as S
+    from keff_cfd_b200.api import structure_from_image
+    d = str(tmp_path)
+    img = S.to_gray(S.disc_image(11, n=32))
+    Image.fromarray(img).save(os.path.join(d, "m.jpg"), quality=95)
+    txt = INPUT_2D.format(amp=1, name="m.jpg", tmap=0, batch=0, nimg=1).replace("MeshFlag: 0", "MeshFlag: 1").replace("MaxMesh: 10", "MaxMesh: 3")
+    open(os.path.join(d, "input.txt"), "w").write(txt)
+    r = subprocess.run([os.path.join(built, "keff2D")], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    rows = [l.split(",") for l in open(os.path.join(d, "batchTest.csv")).read().strip().splitlines()]
+    assert len(rows) == 3 and [int(x[6]) for x in rows] == [32 * 32, 64 * 64, 96 * 96]
+    for m, row in zip((1, 2, 3), rows):
+        want = R.orc_discrete(S.to_gray(structure_from_image(img, m, m)))["keff"]
+        assert abs(float(row[0]) - want) / want < 1e-5, (m, row[0], want)
+    assert int(rows[1][3]) <= int(rows[0][3]) and int(rows[2][3]) <= int(rows[0][3])      # warm starts help
+    # 3D: a small volume, m = 1, 2; plus the Q-map the reference never wrote
+    vol = S.bernoulli_volume((6, 8, 10), 0.4, 3)
+    z, y, x = np.nonzero(vol)
+    np.savetxt(os.path.join(d, "vol.csv"), np.stack([x, y, z], 1), fmt="%d", delimiter=",")
+    base = ("Input File:\nks: 10\nkf: 1\nWidth: 10\nHeight: 8\nDepth: 6\nMeshAmpX: 1\nMeshAmpY: 1\nMeshAmpZ: 1\n"
+            "InputName: vol.csv\nTR: 1\nTL: 0\nOutputName: out3.csv\nprintTMap: 0\nTMapName: T3.csv\nprintQMap: {q}\nQMapName: Q3.csv\n"
+            "Convergence: 0.00001\nMaxIter: 500000\nVerbose: 0\nNumCores: 1\nMeshFlag: {mf}\nMaxMesh: 2\nRunBatch: 0\nNumImages: 1\n")
+    open(os.path.join(d, "in3.txt"), "w").write(base.format(q=0, mf=1))
+    r = subprocess.run([os.path.join(built, "keff3D"), "in3.txt"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    rows = [l.split(",") for l in open(os.path.join(d, "out3.csv")).read().strip().splitlines()]
+    assert len(rows) == 2 and [int(x[6]) for x in rows] == [480, 3840]
+    for m, row in zip((1, 2), rows):
+        amp = np.repeat(np.repeat(np.repeat(vol, m, axis=0), m, axis=1), m, axis=2)
+        want = R.orc_discrete(amp)["keff"]
+        assert abs(float(row[0]) - want) / want < 1e-5, (m, row[0], want)
+    os.remove(os.path.join(d, "out3.csv"))
+    open(os.path.join(d, "in3.txt"), "w").write(base.format(q=1, mf=0))
+    r = subprocess.run([os.path.join(built, "keff3D"), "in3.txt"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0 and "not currently available" not in r.stdout, r.stderr + r.stdout
+    q = open(os.path.join(d, "Q3.csv")).read().splitlines()
+    assert q[0] == "x,y,z,Q" and len(q) == 1 + 6 * 8 * 11
+    keff = float(open(os.path.join(d, "out3.csv")).read().split(",")[0])
+    flux = np.array([float(l.split(",")[3]) for l in q[1:]]).reshape(6, 8, 11)
+    assert np.abs(flux.sum(axis=(0, 1)) - keff).max() < 1e-4                                # every plane carries Keff * (TR - TL)
+
+
+@pytest.mark.gpu
+def test_keff2d_batch_uses_every_gpu(built, tmp_path, R):
+    """Batch mode binds every visible GPU (keffb200_init_multi) and shards each chunk over them."""
+    import torch
+    from PIL import Image
+    from keff_cfd_b200 import structures as S
+    n_gpu = torch.cuda.device_count()
+    d = str(tmp_path)
+    n_img = 256
+    for i in range(n_img):
+        Image.fromarray(S.to_gray(S.disc_image(i, n=32))).save(os.path.join(d, "%05d.jpg" % i), quality=95)
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name="x.jpg", tmap=0, batch=1, nimg=n_img))
+    r = subprocess.run([os.path.join(built, "keff2D")], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"{n_gpu} GPU" in r.stdout, r.stdout
+    rows = [l.split(",") for l in open(os.path.join(d, "batchTest.csv")).read().strip().splitlines()]
+    assert len(rows) == n_img
+    for i in (0, 100, 255):                                                                  # first, middle, last shard
+        want = R.orc_discrete(S.to_gray(S.disc_image(i, n=32)))["keff"]
+        assert abs(float(rows[i][0]) - want) / want < 1e-5
