@@ -185,7 +185,50 @@ def cpu_other_configs(refbind, api, p):
                                                "takes 14 600 sweeps: tests/golden/ref3d_schwarz163.json)"}
     except Exception as e:
         out["config2_schwarz163"] = {"error": repr(e)}
+    out["ref_gpu_program_00000"] = ref_gpu_program(api, p)
     return out
+
+
+def ref_gpu_program(api, p):
+    """The reference's OWN GPU program (Keff2DGPU/keff2D.cu: FP32 Jacobi through updateX_V1, host-side Residual every
+    10^4 / 10^3 iterations, keff2D.cuh:726-849), unmodified, compiled for sm_100 into oracle/_ref by oracle/Makefile, on
+    its shipped input (00000.jpg, MeshAmp 2 -> 256 x 256, Convergence 1e-5) -- the program this path replaces -- with
+    keffb200_solve2d on the same structure beside it."""
+    import shutil
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "keff2DGPU")
+    jpg = os.path.join(ROOT, "tests", "golden", "inputs", "00000.jpg")
+    if not (os.path.exists(exe) and os.path.exists(jpg)):
+        return {"unavailable": "oracle/_ref/keff2DGPU was not built (needs /root/reference and nvcc)"}
+    d = tempfile.mkdtemp()
+    try:
+        shutil.copy(jpg, d)
+        open(os.path.join(d, "input.txt"), "w").write(
+            "Input File:\nks: 10\nkf: 1\nMeshAmpX: 2\nMeshAmpY: 2\nInputName: 00000.jpg\nTR: 1\nTL: 0\nOutputName: batchTest.csv\n"
+            "printTMap: 0\nTMapName: T.csv\nprintQMap: 0\nQMapName: Q.csv\nConvergence: 0.00001\nMaxIter: 500000\nVerbose: 0\n"
+            "NumCores: 1\nMeshFlag: 0\nMaxMesh: 1\nRunBatch: 0\nNumImages: 1\n")
+        t0 = time.perf_counter()
+        r = subprocess.run([exe], cwd=d, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=300)
+        wall = time.perf_counter() - t0
+        rec = {"kind": "reference GPU program (unmodified, sm_100)", "wall_seconds": wall, "returncode": r.returncode}
+        try:
+            row = open(os.path.join(d, "batchTest.csv")).read().strip().splitlines()[-1].split(",")
+            rec.update({"keff_printed": float(row[2]), "gpu_seconds": float(row[3]), "cells": int(row[4]), "residual": float(row[5])})
+        except Exception as e:
+            rec["row_error"] = repr(e) + " | " + r.stdout[-300:]
+        img = np.load(os.path.join(ROOT, "tests", "golden", "img_00000.npy"))
+        solid = api.structure_from_image(img, 2, 2)
+        api.solve2d(solid, p, want_T=False)
+        g = api.solve2d(solid, p, want_T=False)
+        rec.update({"keffb200_gpu_ms": g["gpu_ms"], "keffb200_iters": g["iters"], "keffb200_keff": g["keff"],
+                    "discrete_keff": 4.9003936365, "sample": "Keff2DGPU shipped input: 00000.jpg, MeshAmp 2 (256 x 256), Convergence 1e-5"})
+        if "gpu_seconds" in rec and g["gpu_ms"] > 0:
+            rec["speedup_device_time"] = rec["gpu_seconds"] * 1e3 / g["gpu_ms"]
+        return rec
+    except Exception as e:
+        return {"error": repr(e)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def main():
