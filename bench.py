@@ -483,13 +483,21 @@ def main():
         if rank == 0:
             full = api.bernoulli_volume_dev((npar, npar, npar), 0.5, 1234, device=local)
             s1 = api.solve3d(full, ps, device=local)
-            Tfull = torch.cat(parts)
+            torch.cuda.synchronize()
+            per_slab = [float((parts[q] - s1["T"][q * nzlp:(q + 1) * nzlp]).abs().max().item()) for q in range(world)]
             out["slab_parity"] = {"workload": f"256^3 random binary volume: {world} z-slabs vs the same solve on one GPU",
                                   "keff_slab": rp["keff"], "keff_single": s1["keff"],
                                   "keff_rel_diff": abs(rp["keff"] - s1["keff"]) / abs(s1["keff"]),
-                                  "T_maxdiff": float((Tfull - s1["T"]).abs().max().item()),
+                                  "T_maxdiff": max(per_slab), "T_maxdiff_per_slab": per_slab,
+                                  "rel_residual_slab": rp["rel_residual"], "rel_residual_single": s1["rel_residual"],
                                   "iters_slab": rp["iters"], "iters_single": s1["iters"], "status": rp["status"]}
-            del full, s1, Tfull
+            if max(per_slab) > 1e-6:                                # diagnostics for the record: which field is off, and how
+                out["slab_parity"]["diagnostic"] = {
+                    "single_T_range": [float(s1["T"].min().item()), float(s1["T"].max().item())],
+                    "single_T_zeros": int((s1["T"] == 0).sum().item()),
+                    "slab_T_ranges": [[float(q.min().item()), float(q.max().item())] for q in parts],
+                    "slab_T_zeros": [int((q == 0).sum().item()) for q in parts]}
+            del full, s1
         del parts, rp
         torch.cuda.empty_cache()
         barrier()

@@ -445,14 +445,18 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
         float4 a0 = arow[0], a1 = arow[1];
         const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        // a row whose entry in the pivot column is zero does not change (the matrix is banded: rows beyond
+        // k + nax have not been reached by the fill yet) -- a third of all row updates
+        if (ci != 0.f || gi == k) {
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-          const float rj = gj + jj == k ? pinv : rr[jj] * pinv;
-          const float keep = gj + jj == k ? 0.f : av[jj];
-          av[jj] = gi == k ? rj : keep - ci * rj;
+          for (int jj = 0; jj < 8; jj++) {
+            const float rj = gj + jj == k ? pinv : rr[jj] * pinv;
+            const float keep = gj + jj == k ? 0.f : av[jj];
+            av[jj] = gi == k ? rj : keep - ci * rj;
+          }
+          arow[0] = make_float4(av[0], av[1], av[2], av[3]);
+          arow[1] = make_float4(av[4], av[5], av[6], av[7]);
         }
-        arow[0] = make_float4(av[0], av[1], av[2], av[3]);
-        arow[1] = make_float4(av[4], av[5], av[6], av[7]);
         if (gi == k + 1) {
           *reinterpret_cast<float4*>(nbuf + gj) = make_float4(av[0], av[1], av[2], av[3]);
           *reinterpret_cast<float4*>(nbuf + gj + 4) = make_float4(av[4], av[5], av[6], av[7]);

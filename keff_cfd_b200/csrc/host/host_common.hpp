@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../../include/keffb200.h"
-#include "jpeg_gray.hpp"
+#include "image_gray.hpp"
 
 namespace kbhost {
 

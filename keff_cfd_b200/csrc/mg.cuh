@@ -179,13 +179,11 @@ __global__ void __launch_bounds__(256) k_mg_restrict(const MgLevelView L, const 
             const int x = fx ? 2 * X + dx : X;
             if (x >= L.nx) break;
             const int i = (z * L.ny + y) * L.nx + x;
-            float q = 0.f;
-            if (x > 0) q += L.cx[i - 1] * in[i - 1];
-            if (x < L.nx - 1) q += L.cx[i] * in[i + 1];
-            if (y > 0) q += L.cy[i - L.nx] * in[i - L.nx];
-            if (y < L.ny - 1) q += L.cy[i] * in[i + L.nx];
-            if (z > 0 || lo) q += L.cz[i - plane] * in[i - plane];
-            if (z < L.nz - 1 || hi) q += L.cz[i] * in[i + plane];
+            // no boundary branches: the conductance of a face that leaves the domain is zero by construction (so is
+            // cz[plane -1] without a lower neighbour, from the pool memset) and the value it multiplies is finite
+            // (spare planes of every level array are zeroed at setup), so all 13 loads go out together
+            const float q = ((L.cx[i - 1] * in[i - 1] + L.cx[i] * in[i + 1]) + (L.cy[i - L.nx] * in[i - L.nx] + L.cy[i] * in[i + L.nx])) +
+                            (L.cz[i - plane] * in[i - plane] + L.cz[i] * in[i + plane]);
             acc += __fdividef(as * in[i] + K.b * u[i], L.dinv[i]) + gs * q;
           }
         }
@@ -222,22 +220,17 @@ __global__ void __launch_bounds__(256) k_mg_sweep(const MgLevelView L, const flo
     for (int x = tx; x < L.nx; x += bx) {
       const int i = row * L.nx + x;
       const int X = fx ? x >> 1 : x;
-      float q = 0.f;
+      // no boundary branches (see k_mg_restrict): faces that leave the domain carry a zero conductance and meet a
+      // finite value (previous / next row, spare planes), so every load of a cell is issued at once
       if (ADD_E) {
-        if (x > 0) q += L.cx[i - 1] * (sc * in[i - 1] + e0[fx ? (x - 1) >> 1 : x - 1]);
-        if (x < L.nx - 1) q += L.cx[i] * (sc * in[i + 1] + e0[fx ? (x + 1) >> 1 : x + 1]);
-        if (y > 0) q += L.cy[i - L.nx] * (sc * in[i - L.nx] + eN[X]);
-        if (y < L.ny - 1) q += L.cy[i] * (sc * in[i + L.nx] + eS[X]);
-        if (z > 0 || lo) q += L.cz[i - plane] * (sc * in[i - plane] + eF[X]);
-        if (z < L.nz - 1 || hi) q += L.cz[i] * (sc * in[i + plane] + eB[X]);
+        const float q = ((L.cx[i - 1] * (sc * in[i - 1] + e0[fx ? (x - 1) >> 1 : x - 1]) +
+                          L.cx[i] * (sc * in[i + 1] + e0[fx ? (x + 1) >> 1 : x + 1])) +
+                         (L.cy[i - L.nx] * (sc * in[i - L.nx] + eN[X]) + L.cy[i] * (sc * in[i + L.nx] + eS[X]))) +
+                        (L.cz[i - plane] * (sc * in[i - plane] + eF[X]) + L.cz[i] * (sc * in[i + plane] + eB[X]));
         out[i] = K.a * (sc * in[i] + e0[X]) + K.b * u[i] + K.g * L.dinv[i] * q;
       } else {
-        if (x > 0) q += L.cx[i - 1] * in[i - 1];
-        if (x < L.nx - 1) q += L.cx[i] * in[i + 1];
-        if (y > 0) q += L.cy[i - L.nx] * in[i - L.nx];
-        if (y < L.ny - 1) q += L.cy[i] * in[i + L.nx];
-        if (z > 0 || lo) q += L.cz[i - plane] * in[i - plane];
-        if (z < L.nz - 1 || hi) q += L.cz[i] * in[i + plane];
+        const float q = ((L.cx[i - 1] * in[i - 1] + L.cx[i] * in[i + 1]) + (L.cy[i - L.nx] * in[i - L.nx] + L.cy[i] * in[i + L.nx])) +
+                        (L.cz[i - plane] * in[i - plane] + L.cz[i] * in[i + plane]);
         out[i] = K.a * sc * in[i] + K.b * u[i] + K.g * sc * L.dinv[i] * q;
       }
     }
