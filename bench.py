@@ -421,6 +421,17 @@ def main():
                             "achieved": gb, "peak": peak, "unit": "GB/s", "frac": gb / peak,
                             "algorithmic_bytes_per_launch": 16.0 * n3 ** 3,
                             "traffic": ncu_traffic("k_stencil_tma_apply", n3 ** 3)}
+        try:                                                        # the same kernel as the multigrid iteration launches it
+            pf = api.default_params(flags=32)                         # KEFFB200_F_APPLY_F32: p stored in FP32
+            msf = api.bench_apply(vol, pf, reps=20, device=local)
+            gbf = 12.0 * n3 ** 3 / (msf * 1e-3) / 1e9
+            out["stencil3d_f32in"] = {"workload": "configs[3], input field in FP32 (p of the multigrid-preconditioned iteration)",
+                                      "kernel": "k_stencil_tma<APPLY, float>", "ms_per_sweep": msf,
+                                      "gcell_updates_per_s": n3 ** 3 / (msf * 1e-3) / 1e9, "bound": "hbm", "achieved": gbf,
+                                      "peak": peak, "unit": "GB/s", "frac": gbf / peak,
+                                      "algorithmic_bytes_per_launch": 12.0 * n3 ** 3}
+        except Exception as e:
+            out["stencil3d_f32in"] = {"error": repr(e)}
         api.solve3d(vol, p, want_T=False, device=local)               # first call allocates the workspace
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -67,6 +67,9 @@ typedef struct keffb200_params {
                                     grid has fewer than 65 cells, ny < 2, or z-slabs are unequal) */
 #define KEFFB200_F_ZERO_INIT 2   /* start from T = tl everywhere (the reference's actual T0,
                                     Keff2D/keff2D.h:584-611) instead of the linear ramp */
+#define KEFFB200_F_APPLY_F32 32   /* keffb200_bench_apply_dev only: time the stencil kernel in the form the multigrid
+                                    iteration launches it (input field p stored in FP32: 12 B per cell-update instead
+                                    of 16); needs nx % 4 == 0 */
 
 /* Per-solve record: the numbers the reference puts in its CSV row (keff, QL, QR, Iter:
  * Keff2D/keff2D.h:245-246) plus what its GPU variant keeps in simulationInfo

@@ -144,6 +144,28 @@ __global__ void __launch_bounds__(256) k_stencil_plain(const double* __restrict_
 constexpr int TX = 64, TY = 16, BOXW = TX + 4, BOXH = TY + 2, NST = 4, NTHR = 256;
 constexpr int STAGE_BYTES = BOXW * BOXH * 8;
 constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+__global__ void k_f64_to_f32(const double* __restrict__ in, float* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+
+// staged plane of the TMA stencil kernel per input type.  FP64 input (x, and p of the diagonally preconditioned path):
+// box of TX + 4 doubles starting 2 cells left of the tile.  FP32 input (p of the multigrid path, which is built from
+// the FP32 z anyway): box of TX + 8 floats starting 4 cells left, so that box rows stay multiples of 16 bytes.
+template <typename T>
+struct StencilTile;
+template <>
+struct StencilTile<double> {
+  static constexpr int boxw = BOXW, hx = 2, bytes = STAGE_BYTES, stride = STAGE_STRIDE;
+};
+template <>
+struct StencilTile<float> {
+  static constexpr int boxw = TX + 8, hx = 4, bytes = (TX + 8) * BOXH * 4, stride = (bytes + 127) / 128 * 128;
+};
+__device__ __forceinline__ double2 tile_ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 tile_ld2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return make_double2((double)v.x, (double)v.y);
+}
 
 struct Plan {
   int ntx, nty, nzc, zlen, nitems;
@@ -160,12 +182,13 @@ __device__ __forceinline__ void plan_item(const Plan& P, int item, int& tx, int&
 
 __device__ __forceinline__ double pick(bool c, double a, double b) { return c ? a : b; }
 
-template <int MODE>
+template <int MODE, typename TIN = double>
 __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CUtensorMap tm,
                                                       const uint8_t* __restrict__ code, double* __restrict__ o0,
                                                       double* __restrict__ o1, const Coef C, const Dom D, const Plan P,
                                                       const Scal* __restrict__ S, double* __restrict__ partials) {
-  __shared__ __align__(128) unsigned char tiles[NST * STAGE_STRIDE];
+  using TT = StencilTile<TIN>;
+  __shared__ __align__(128) unsigned char tiles[NST * TT::stride];
   __shared__ __align__(8) uint64_t full[NST];
   __shared__ double red[32 * 3];
   if (S->done) return;
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
   uint32_t seq = 0;  // planes streamed so far by this CTA (identical in every thread)
   double acc[3] = {0, 0, 0};
   const long plane = (long)D.nx * D.ny;
-  const int coff = (ly + 1) * BOXW + lx + 2;  // cell a of my 2x2 block inside a staged plane
+  const int coff = (ly + 1) * TT::boxw + lx + TT::hx;  // cell a of my 2x2 block inside a staged plane
   // interior "same phase" conductances [phase]
   const double sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0], sy1 = C.same[1][1];
   const double sz0 = C.same[2][0], sz1 = C.same[2][1];
@@ -204,9 +227,9 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
       const int npre = min(NST, nplanes);
       for (int k = 0; k < npre; k++) {
         const uint32_t st = (seq + k) % NST;
-        mbar_expect_tx(&full[st], STAGE_BYTES);
+        mbar_expect_tx(&full[st], TT::bytes);
         // tensor z index = local plane + 1 (field arrays carry one halo plane below plane 0)
-        tma_load_3d(tiles + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + k);
+        tma_load_3d(tiles + st * TT::stride, &tm, &full[st], xo - TT::hx, yo - 1, zb + k);
       }
     }
     long ci = ((long)zb * D.ny + gy) * D.nx + gx;  // global index of cell a in plane zb
@@ -217,12 +240,12 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
     {
       const uint32_t q0 = seq % NST, q1 = (seq + 1) % NST;
       mbar_wait(&full[q0], (seq / NST) & 1);
-      const double* lo = reinterpret_cast<const double*>(tiles + q0 * STAGE_STRIDE) + coff;
-      const double2 mt = *reinterpret_cast<const double2*>(lo), mb = *reinterpret_cast<const double2*>(lo + BOXW);
+      const TIN* lo = reinterpret_cast<const TIN*>(tiles + q0 * TT::stride) + coff;
+      const double2 mt = tile_ld2(lo), mb = tile_ld2(lo + TT::boxw);
       mbar_wait(&full[q1], ((seq + 1) / NST) & 1);
-      const double* c0 = reinterpret_cast<const double*>(tiles + q1 * STAGE_STRIDE) + coff;
-      pt = *reinterpret_cast<const double2*>(c0);
-      pb = *reinterpret_cast<const double2*>(c0 + BOXW);
+      const TIN* c0 = reinterpret_cast<const TIN*>(tiles + q1 * TT::stride) + coff;
+      pt = tile_ld2(c0);
+      pb = tile_ld2(c0 + TT::boxw);
       if (D.z0 + zb != 0) {  // face between plane zb-1 and zb
         const unsigned ca = cn0 & 0xffu, cb = cn0 >> 8, cc = cn1 & 0xffu, cd = cn1 >> 8;
         ga = pick(ca & C_F, dfz, pick(ca & C_PH, sz1, sz0)) * (mt.x - pt.x);
@@ -237,23 +260,23 @@ __global__ void __launch_bounds__(NTHR) k_stencil_tma(const __grid_constant__ CU
       __syncthreads();  // every thread is done with plane k-1's stage
       if (tid == 0 && k - 1 + NST < nplanes) {
         const uint32_t st = (seq + k - 1) % NST;  // == stage of plane k-1+NST
-        mbar_expect_tx(&full[st], STAGE_BYTES);
-        tma_load_3d(tiles + st * STAGE_STRIDE, &tm, &full[st], xo - 2, yo - 1, zb + k - 1 + NST);
+        mbar_expect_tx(&full[st], TT::bytes);
+        tma_load_3d(tiles + st * TT::stride, &tm, &full[st], xo - TT::hx, yo - 1, zb + k - 1 + NST);
       }
       const uint32_t sc = (seq + k) % NST, sn = (seq + k + 1) % NST;
       mbar_wait(&full[sn], ((seq + k + 1) / NST) & 1);
-      const double* cur = reinterpret_cast<const double*>(tiles + sc * STAGE_STRIDE) + coff;
-      const double* nxt = reinterpret_cast<const double*>(tiles + sn * STAGE_STRIDE) + coff;
-      nt = *reinterpret_cast<const double2*>(nxt);
-      nb = *reinterpret_cast<const double2*>(nxt + BOXW);
+      const TIN* cur = reinterpret_cast<const TIN*>(tiles + sc * TT::stride) + coff;
+      const TIN* nxt = reinterpret_cast<const TIN*>(tiles + sn * TT::stride) + coff;
+      nt = tile_ld2(nxt);
+      nb = tile_ld2(nxt + TT::boxw);
       const unsigned k0 = cn0, k1 = cn1;
       if (k < len) {
         if (row0) cn0 = *reinterpret_cast<const unsigned short*>(code + ci + plane);
         if (row1) cn1 = *reinterpret_cast<const unsigned short*>(code + ci + plane + D.nx);
       }
-      const double2 pn = *reinterpret_cast<const double2*>(cur - BOXW);
-      const double2 ps = *reinterpret_cast<const double2*>(cur + 2 * BOXW);
-      const double pwt = cur[-1], pet = cur[2], pwb = cur[BOXW - 1], peb = cur[BOXW + 2];
+      const double2 pn = tile_ld2(cur - TT::boxw);
+      const double2 ps = tile_ld2(cur + 2 * TT::boxw);
+      const double pwt = cur[-1], pet = cur[2], pwb = cur[TT::boxw - 1], peb = cur[TT::boxw + 2];
       const unsigned ca = k0 & 0xffu, cb = k0 >> 8, cc = k1 & 0xffu, cd = k1 >> 8;
       const bool fa = ca & C_PH, fb = cb & C_PH, fc = cc & C_PH, fd = cd & C_PH;
       // start from the flux that entered from the plane below

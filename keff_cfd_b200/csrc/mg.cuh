@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
 // CG vector kernels of the multigrid-preconditioned iteration.
 //   k_cg_update_mg<1>: r -= alpha q;  u = r / d (FP32);  partial r.r                       (29 B per cell)
 //   k_cg_update_mg<0>: u = r / d alone (after the initial residual, and for the test hook)
-//   k_cg_dir_mg      : x += alpha p;  p = z + beta p  (z is FP32; first = 1: p = z only)     (36 B per cell)
+//   k_cg_dir_mg      : x += alpha p;  p = z + beta p  (z is FP32; first = 1: p = z only)     (36 B per cell; 28 with p in FP32)
 // x += alpha p rides with the direction update because that kernel reads p anyway (p is then read
 // once per iteration instead of twice).  It must happen exactly once per completed residual update
 // even though every kernel of the blindly enqueued iterations after convergence returns early: the
@@ -694,10 +694,23 @@ __global__ void __launch_bounds__(256) k_cg_update_mg(double* __restrict__ r, co
   }
 }
 
-__global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, double* __restrict__ p,
+template <typename TP>
+struct Pair2;
+template <>
+struct Pair2<double> { using type = double2; };
+template <>
+struct Pair2<float> { using type = float2; };
+
+// TP: storage type of p.  double: as the other CG vectors.  float: p = z + beta p is built from the FP32 z, and x, r
+// are both advanced with the SAME stored p (x += alpha p here, r -= alpha A p from the stencil of that p), so r stays
+// the residual of x to FP64 rounding -- rounding p only perturbs the search direction (by 6e-8, next to the FP32
+// preconditioner) and saves 12 of the iteration's 131 bytes per cell.
+template <typename TP>
+__global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, TP* __restrict__ p,
                                                    const float* __restrict__ z, long n2, long n,
                                                    const Scal* __restrict__ S, int par, long long kit, int first,
                                                    const HaloPush H, long plane2) {
+  using P2 = typename Pair2<TP>::type;
   const bool upd_x = !first && S->it == kit + 1, upd_p = !S->done;
   const bool push = (H.lo_dst || H.hi_dst) && n2 >= 2 * plane2;
   if (!upd_x && !upd_p) {
@@ -706,19 +719,21 @@ __global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, doubl
   }
   const double alpha = upd_x ? S->rz[par] / S->pq : 0.0;
   const double beta = first ? 0.0 : S->rz[par ^ 1] / S->rz[par];
-  auto body = [&](long i, double2* remote) {
-    double2 vp = reinterpret_cast<double2*>(p)[i];
+  auto body = [&](long i, P2* remote) {
+    P2 vp;  // first: p = z, and what the buffer held before (another solve's FP64 values, say) must not be looked at
+    if (first) vp.x = vp.y = (TP)0;
+    else vp = reinterpret_cast<P2*>(p)[i];
     if (upd_x) {
       double2 vx = reinterpret_cast<double2*>(x)[i];
-      vx.x += alpha * vp.x;
-      vx.y += alpha * vp.y;
+      vx.x += alpha * (double)vp.x;
+      vx.y += alpha * (double)vp.y;
       reinterpret_cast<double2*>(x)[i] = vx;
     }
     if (upd_p) {
       const float2 vz = reinterpret_cast<const float2*>(z)[i];
-      vp.x = (double)vz.x + beta * vp.x;
-      vp.y = (double)vz.y + beta * vp.y;
-      reinterpret_cast<double2*>(p)[i] = vp;
+      vp.x = (TP)((double)vz.x + beta * (double)vp.x);
+      vp.y = (TP)((double)vz.y + beta * (double)vp.y);
+      reinterpret_cast<P2*>(p)[i] = vp;
       if (remote) *remote = vp;
     }
   };
@@ -730,15 +745,15 @@ __global__ void __launch_bounds__(256) k_cg_dir_mg(double* __restrict__ x, doubl
     lo = plane2;
     hi = n2 - plane2;
     for (long i = g; i < plane2; i += stride) {
-      body(i, H.lo_dst ? reinterpret_cast<double2*>(H.lo_dst) + i : nullptr);
-      body(hi + i, H.hi_dst ? reinterpret_cast<double2*>(H.hi_dst) + i : nullptr);
+      body(i, H.lo_dst ? reinterpret_cast<P2*>(H.lo_dst) + i : nullptr);
+      body(hi + i, H.hi_dst ? reinterpret_cast<P2*>(H.hi_dst) + i : nullptr);
     }
     halo_signal(H, 1, 1);
   }
   for (long i = lo + g; i < hi; i += stride) body(i, nullptr);
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    if (upd_x) x[n - 1] += alpha * p[n - 1];
-    if (upd_p) p[n - 1] = (double)z[n - 1] + beta * p[n - 1];
+    if (upd_x) x[n - 1] += alpha * (double)p[n - 1];
+    if (upd_p) p[n - 1] = (TP)((double)z[n - 1] + (first ? 0.0 : beta * (double)p[n - 1]));
   }
 }
 

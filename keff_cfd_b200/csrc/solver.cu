@@ -150,29 +150,31 @@ static int reduce_step(int n, int arg) {
   return 0;
 }
 
-// exchange the boundary planes of a halo'ed FP64 field (x or p) with the z neighbours (f points at the halo plane)
-static int exchange_halo(double* f_halo, const Dom& D, cudaStream_t st) {
+// exchange the boundary planes of a halo'ed fine-grid field (x, or p: `esz` bytes per value -- p is FP32 on the
+// multigrid path) with the z neighbours (f points at the halo plane)
+static int exchange_halo(void* f_halo_v, const Dom& D, cudaStream_t st, size_t esz = 8) {
   Ctx& c = ctx();
   Nccl& n = c.nccl;
   if (!c.dist_active) return 0;
-  const size_t plane = (size_t)D.nx * D.ny;
+  const size_t pb = (size_t)D.nx * D.ny * esz;  // bytes per plane
+  char* f_halo = (char*)f_halo_v;
   if (c.link.p2p) {
-    const bool is_x = f_halo == c.x;
-    return link_exchange(c, is_x ? HF_X : HF_P, is_x ? W_X : W_P, (char*)(f_halo + plane), plane * 8, D.nz, true);
+    const bool is_x = f_halo_v == (void*)c.x;
+    return link_exchange(c, is_x ? HF_X : HF_P, is_x ? W_X : W_P, f_halo + pb, pb, D.nz, true);
   }
   if (n.world <= 1 || !n.comm) return 0;
-  double* lo_halo = f_halo;
-  double* first = f_halo + plane;
-  double* last = f_halo + plane * D.nz;
-  double* hi_halo = f_halo + plane * (D.nz + 1);
+  char* lo_halo = f_halo;
+  char* first = f_halo + pb;
+  char* last = f_halo + pb * D.nz;
+  char* hi_halo = f_halo + pb * (D.nz + 1);
   KB_TRY(nccl_check(n.GroupStart(), "ncclGroupStart"));
   if (n.rank > 0) {
-    KB_TRY(nccl_check(n.Send(first, plane, 8, n.rank - 1, n.comm, st), "ncclSend"));
-    KB_TRY(nccl_check(n.Recv(lo_halo, plane, 8, n.rank - 1, n.comm, st), "ncclRecv"));
+    KB_TRY(nccl_check(n.Send(first, pb, /*ncclInt8*/ 0, n.rank - 1, n.comm, st), "ncclSend"));
+    KB_TRY(nccl_check(n.Recv(lo_halo, pb, 0, n.rank - 1, n.comm, st), "ncclRecv"));
   }
   if (n.rank < n.world - 1) {
-    KB_TRY(nccl_check(n.Send(last, plane, 8, n.rank + 1, n.comm, st), "ncclSend"));
-    KB_TRY(nccl_check(n.Recv(hi_halo, plane, 8, n.rank + 1, n.comm, st), "ncclRecv"));
+    KB_TRY(nccl_check(n.Send(last, pb, 0, n.rank + 1, n.comm, st), "ncclSend"));
+    KB_TRY(nccl_check(n.Recv(hi_halo, pb, 0, n.rank + 1, n.comm, st), "ncclRecv"));
   }
   KB_TRY(nccl_check(n.GroupEnd(), "ncclGroupEnd"));
   return 0;
@@ -260,6 +262,8 @@ struct Stencil {
   Dom D{};
   Coef C{};
   CUtensorMap tm_x, tm_p;  // descriptors for the two fields that are ever stencil inputs
+  CUtensorMap tm_p32;      // p stored in FP32 (multigrid path; same buffer as p)
+  bool p32_ok = false;     // tm_p32 is valid (TMA path, nx % 4 == 0: FP32 rows must be multiples of 16 bytes)
 };
 
 static int make_tmap(CUtensorMap* tm, double* field_halo, const Dom& D) {
@@ -272,6 +276,20 @@ static int make_tmap(CUtensorMap* tm, double* field_halo, const Dom& D) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(KEFFB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// FP32 view of a halo'ed field buffer (p on the multigrid path): box of TX + 8 floats starting 4 cells left of the tile
+static int make_tmap_f32(CUtensorMap* tm, float* field_halo, const Dom& D) {
+  Ctx& c = ctx();
+  cuuint64_t dims[3] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nz + 2};
+  cuuint64_t strides[2] = {(cuuint64_t)D.nx * 4, (cuuint64_t)D.nx * D.ny * 4};
+  cuuint32_t box[3] = {(cuuint32_t)StencilTile<float>::boxw, BOXH, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = c.encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, field_halo, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(KEFFB200_ECUDA, "cuTensorMapEncodeTiled (FP32 field) failed (%d)", (int)r);
   return 0;
 }
 
@@ -308,6 +326,9 @@ static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
   if (s.tma) {
     KB_TRY(make_tmap(&s.tm_x, c.x, D));
     KB_TRY(make_tmap(&s.tm_p, c.p, D));
+    static const bool no_p32 = getenv("KEFFB200_P64") != nullptr;  // experiments: keep p in FP64 on the multigrid path
+    s.p32_ok = D.nx % 4 == 0 && !no_p32;
+    if (s.p32_ok) KB_TRY(make_tmap_f32(&s.tm_p32, reinterpret_cast<float*>(c.p), D));
     // experiment switch: the warp-specialised ring (producer warp + full/empty mbarriers, code bytes by TMA).
     // Measured at 512^3 on B200: 0.445 ms (3 CTAs/SM, 72 registers, 6 stages) / 0.433 ms (2 CTAs/SM, 9 stages)
     // against 0.421 ms for the __syncthreads ring, so it is off by default.  Also measured and rejected: a 6-stage
@@ -315,6 +336,7 @@ static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
     // over the grid (0.608 ms: x-adjacent tiles stop streaming the same DRAM rows at the same time).
     static const bool want_ws = getenv("KEFFB200_STENCIL_WS") != nullptr;
     s.ws = want_ws && D.nx % 16 == 0;
+    if (s.ws) s.p32_ok = false;
     int occ = occupancy_tma<MODE_APPLY>();
     if (s.ws) {
       KB_TRY(make_tmap_code(&s.tm_code, c.code, D));
@@ -359,13 +381,16 @@ static int stencil_setup(Stencil& s, const Dom& D, const Coef& C, int flags) {
   return 0;
 }
 
-// in_halo: halo'ed field base; which: 0 -> x, 1 -> p (selects the tensor map)
+// in_halo: halo'ed field base; which: 0 -> x, 1 -> p, 2 -> p stored in FP32 (selects the tensor map)
 template <int MODE>
 static int stencil_launch(const Stencil& s, int which, double* o0, double* o1) {
   Ctx& c = ctx();
   const size_t plane = (size_t)s.D.nx * s.D.ny;
   double* in_halo = which == 0 ? c.x : c.p;
-  if (s.ws) {
+  if (which == 2) {
+    if (MODE != MODE_APPLY || !s.p32_ok) return fail(KEFFB200_ESTATE, "FP32 stencil input outside the multigrid iteration");
+    k_stencil_tma<MODE_APPLY, float><<<s.grid, NTHR, 0, c.st>>>(s.tm_p32, c.code, o0, o1, s.C, s.D, s.plan, c.S, c.partials);
+  } else if (s.ws) {
     k_stencil_ws<MODE><<<s.grid, WS_THR, WS_SMEM, c.st>>>(which == 0 ? s.tm_x : s.tm_p, s.tm_code, o0, o1, s.C, s.D, s.plan, c.S,
                                                           c.partials);
   } else if (s.tma) {
@@ -859,6 +884,9 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   KB_CUDA(cudaMemsetAsync(c.x + plane * (D.nz + 1), 0, plane * 8, c.st));
   KB_CUDA(cudaMemsetAsync(c.p, 0, plane * 8, c.st));
   KB_CUDA(cudaMemsetAsync(c.p + plane * (D.nz + 1), 0, plane * 8, c.st));
+  // (p is stored in FP32 on the multigrid path, decided below: its upper halo plane then sits at half the offset;
+  //  in the FP64 layout that is interior, which the first direction update rewrites)
+  KB_CUDA(cudaMemsetAsync(reinterpret_cast<float*>(c.p) + plane * (D.nz + 1), 0, plane * 4, c.st));
   // z-slabs over peer memory: meet the group (everybody has finished its previous solve), clear my arrival
   // counters, publish where my workspace lives and learn where the neighbours' does
   if (c.dist_active && c.link.p2p) KB_TRY(link_publish(c, D, true));
@@ -886,6 +914,10 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   if (mg_eligible(D, P.flags)) KB_TRY(mg_setup(mg, D, C));
   const long n2 = (long)(n / 2);
   const int gm = mg_grid(n2);
+  // p in FP32 on the multigrid path (x and r advance with the same stored p, so r stays the residual of x)
+  const bool p32 = mg.on && s.p32_ok;
+  const size_t pesz = p32 ? 4 : 8;
+  float* pf = reinterpret_cast<float*>(c.p) + plane;
   // iterations between two convergence records.  The multigrid path takes ~10 iterations of milliseconds: it
   // records every iteration; the diagonally preconditioned path takes thousands of short ones.
   const long batch_len = mg.on ? 1 : P.check_every;
@@ -910,8 +942,9 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       KB_TRY(mg_make_u(mg, r));
       KB_TRY(mg_vcycle(mg, c.z));
       KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, 0));
-      const Fused f = fused_push(HF_P, W_P, plane * 8, D.nz);
-      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1, f.H, (long)(plane / 2));
+      const Fused f = fused_push(HF_P, W_P, plane * pesz, D.nz);
+      if (p32) k_cg_dir_mg<float><<<gm, 256, 0, c.st>>>(x, pf, c.z, n2, (long)n, c.S, 0, -1, 1, f.H, (long)(plane / 2));
+      else k_cg_dir_mg<double><<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, 0, -1, 1, f.H, (long)(plane / 2));
       KB_LAUNCHED();
       p_pushed = f.on;
       KB_TRY(fused_wait(f, (unsigned)gm));
@@ -921,8 +954,8 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   // iteration k since the last (re)start; every kernel returns at once when the stop flag is up
   auto enqueue_iter = [&](long k) -> int {
     const int par = (int)(k & 1);
-    if (!p_pushed) KB_TRY(exchange_halo(c.p, D, c.st));
-    KB_TRY(stencil_launch<MODE_APPLY>(s, 1, q, nullptr));
+    if (!p_pushed) KB_TRY(exchange_halo(c.p, D, c.st, pesz));
+    KB_TRY(stencil_launch<MODE_APPLY>(s, p32 ? 2 : 1, q, nullptr));
     KB_TRY(reduce_step<RS_PQ>(s.grid, 0));
     if (mg.on) {
       const Fused fu = fused_push(HF_U, W_U, (size_t)mg.pitch * D.ny * sizeof(float), D.nz);
@@ -934,8 +967,9 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
       KB_TRY(fused_wait(fu, (unsigned)mg.gu));
       KB_TRY(mg_vcycle(mg, c.z));
       KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, par ^ 1));
-      const Fused fp = fused_push(HF_P, W_P, plane * 8, D.nz);
-      k_cg_dir_mg<<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0, fp.H, (long)(plane / 2));
+      const Fused fp = fused_push(HF_P, W_P, plane * pesz, D.nz);
+      if (p32) k_cg_dir_mg<float><<<gm, 256, 0, c.st>>>(x, pf, c.z, n2, (long)n, c.S, par, (long long)k, 0, fp.H, (long)(plane / 2));
+      else k_cg_dir_mg<double><<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0, fp.H, (long)(plane / 2));
       KB_LAUNCHED();
       p_pushed = fp.on;
       KB_TRY(fused_wait(fp, (unsigned)gm));
@@ -1623,9 +1657,17 @@ int keffb200_bench_apply_dev(const uint8_t* d_solid, int nx, int ny, int nz, con
   KB_CUDA(cudaMemsetAsync(c.S, 0, sizeof(Scal), c.st));
   Stencil s;
   KB_TRY(stencil_setup(s, D, C, P.flags));
-  for (int i = 0; i < 3; i++) KB_TRY(stencil_launch<MODE_APPLY>(s, 1, c.q + plane, nullptr));
+  int which = 1;
+  if (P.flags & KEFFB200_F_APPLY_F32) {  // the form the multigrid iteration uses: p stored in FP32
+    if (!s.p32_ok) return fail(KEFFB200_EINVAL, "KEFFB200_F_APPLY_F32 needs the TMA path and nx %% 4 == 0");
+    KB_CUDA(cudaMemcpyAsync(c.r, c.p, plane * (nz + 2) * 8, cudaMemcpyDeviceToDevice, c.st));
+    k_f64_to_f32<<<c.sms * 8, 256, 0, c.st>>>(c.r, reinterpret_cast<float*>(c.p), (long)(plane * (nz + 2)));
+    KB_LAUNCHED();
+    which = 2;
+  }
+  for (int i = 0; i < 3; i++) KB_TRY(stencil_launch<MODE_APPLY>(s, which, c.q + plane, nullptr));
   KB_CUDA(cudaEventRecord(c.ev0, c.st));
-  for (int i = 0; i < reps; i++) KB_TRY(stencil_launch<MODE_APPLY>(s, 1, c.q + plane, nullptr));
+  for (int i = 0; i < reps; i++) KB_TRY(stencil_launch<MODE_APPLY>(s, which, c.q + plane, nullptr));
   KB_CUDA(cudaEventRecord(c.ev1, c.st));
   KB_CUDA(cudaStreamSynchronize(c.st));
   float ms = 0;
