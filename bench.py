@@ -429,7 +429,8 @@ def main():
                                       "kernel": "k_stencil_tma<APPLY, float>", "ms_per_sweep": msf,
                                       "gcell_updates_per_s": n3 ** 3 / (msf * 1e-3) / 1e9, "bound": "hbm", "achieved": gbf,
                                       "peak": peak, "unit": "GB/s", "frac": gbf / peak,
-                                      "algorithmic_bytes_per_launch": 12.0 * n3 ** 3}
+                                      "algorithmic_bytes_per_launch": 12.0 * n3 ** 3,
+                                      "traffic": ncu_traffic("k_stencil_tma_apply_f32in", n3 ** 3)}
         except Exception as e:
             out["stencil3d_f32in"] = {"error": repr(e)}
         api.solve3d(vol, p, want_T=False, device=local)               # first call allocates the workspace

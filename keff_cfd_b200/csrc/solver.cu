@@ -452,6 +452,10 @@ static dim3 mg_row_grid(int nx, int ny, int nz) {
   return dim3((unsigned)gx, (unsigned)std::min(gz, 65535), 1);
 }
 
+static bool mg_prolong_on_the_fly() {  // experiments: KEFFB200_MG_PROLONG_FUSED=1 keeps the on-the-fly prolongation
+  static const bool v = getenv("KEFFB200_MG_PROLONG_FUSED") != nullptr;
+  return v;
+}
 static MgLevelView mg_view(const MgLevel& L) { return MgLevelView{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.dinv}; }
 
 static int mg_setup(Mg& mg, const Dom& D, const Coef& C) {
@@ -843,7 +847,17 @@ static int mg_vcycle(const Mg& mg, float* z) {
     for (int k = nu - 1; k >= 0; k--) {
       float* out = k == 0 ? L.e : (in == L.t0 ? L.t1 : L.t0);
       const MgPass K{s1, 1.f - w[k], w[k], w[k]};
-      if (k == nu - 1)
+      if (k == nu - 1 && in != L.u && s1 == 1.f && !mg_prolong_on_the_fly()) {
+        // the iterate is a stored array of its own (nu >= 2): add P e to it in place (halo planes included), then sweep
+        float* xin = in == L.t0 ? L.t0 : L.t1;
+        const int zf = llo ? -1 : 0, zl = L.nz - 1 + (lhi ? 1 : 0);
+        dim3 gp = gl;
+        gp.y = (unsigned)std::max(1, std::min<int>(zl - zf + 1, (int)gl.y));
+        k_mg_prolong_add<<<gp, 256, 0, c.st>>>(L.nx, L.ny, zf, zl, xin, N.e + on, L.fx, L.fy, L.fz, N.nx, N.ny, mg_bx(L.nx), c.S);
+        KB_LAUNCHED();
+        k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, llo, lhi,
+                                            mg_bx(L.nx), c.S);
+      } else if (k == nu - 1)
         k_mg_sweep<1><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, N.e + on, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, llo, lhi,
                                             mg_bx(L.nx), c.S);
       else
