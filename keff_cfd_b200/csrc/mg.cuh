@@ -336,6 +336,11 @@ constexpr int MG_NST = 6, MG_BOXW = TX + 8, MG_HX = 4;
 constexpr int MG_STAGE_BYTES = MG_BOXW * BOXH * 4;
 constexpr int MG_STAGE_STRIDE = (MG_STAGE_BYTES + 127) / 128 * 128;
 
+// face conductances of the voxel grid rounded to FP32 (what the FP32 cycle works with)
+struct MgCoefF {
+  float same[3][2], diff[3];
+};
+
 struct MgFine {
   const float* e1;     // level-1 correction (ADD_E)
   float* u1;           // level-1 scaled right-hand side (OUT 0)
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
                                                      const uint8_t* __restrict__ code, const float* __restrict__ gtab,
                                                      const float* __restrict__ uown, float* __restrict__ fout,
                                                      float* __restrict__ zout, const MgFine M, const MgPass K,
-                                                     const Coef C, const Dom D, const Plan P,
+                                                     const MgCoefF C, const Dom D, const Plan P,
                                                      const Scal* __restrict__ S, double* __restrict__ partials,
                                                      const HaloPush H) {
   __shared__ __align__(128) unsigned char tiles[MG_NST * MG_STAGE_STRIDE];
@@ -399,14 +404,14 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     mbar_fence_init();
   }
   for (int e = tid; e < MG_TAB; e += NTHR) tab[e] = gtab[(OUT == 0 ? MG_TAB : 0) + e];
-  uint32_t seq = 0;
+  uint32_t rs = 0, rp = 0;  // ring slot and mbarrier parity of the next plane this CTA consumes (identical in every thread)
   double acc[3] = {0, 0, 0};
   const long plane = (long)D.nx * D.ny, pplane = (long)M.pitch * D.ny;
   const int coff = (ly + 1) * MG_BOXW + lx + MG_HX;
   const float sc = K.sc, as = K.a * K.sc, gs = K.g * K.sc;
-  const float sx0 = (float)C.same[0][0], sx1 = (float)C.same[0][1], sy0 = (float)C.same[1][0];
-  const float sy1 = (float)C.same[1][1], sz0 = (float)C.same[2][0], sz1 = (float)C.same[2][1];
-  const float dfx = (float)C.diff[0], dfy = (float)C.diff[1], dfz = (float)C.diff[2];
+  const float sx0 = C.same[0][0], sx1 = C.same[0][1], sy0 = C.same[1][0];
+  const float sy1 = C.same[1][1], sz0 = C.same[2][0], sz1 = C.same[2][1];
+  const float dfx = C.diff[0], dfy = C.diff[1], dfz = C.diff[2];
 
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     int tx, ty, zc;
@@ -430,10 +435,11 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     __syncthreads();  // ring idle (previous item consumed; barriers and table initialised)
     if (tid == 0) {
       const int npre = min(MG_NST, nplanes);
+      uint32_t st = rs;
       for (int k = 0; k < npre; k++) {
-        const uint32_t st = (seq + k) % MG_NST;
         mbar_expect_tx(&full[st], MG_STAGE_BYTES);
         tma_load_3d(tiles + st * MG_STAGE_STRIDE, &tm, &full[st], xo - MG_HX, yo - 1, zb + k);
+        st = st + 1 == MG_NST ? 0 : st + 1;
       }
     }
     long ci = ((long)zb * D.ny + gy) * D.nx + gx;    // global index of cell a in plane zb
@@ -466,14 +472,15 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     }
     float2 pt, pb, lt, lb;  // current plane (top row a,b / bottom row c,d) and the plane below
     float fa, fb, fc, fd;   // conductances of the faces towards the plane below
+    // slots of the plane below the chunk (sprev), of plane k (scur, parity pcur) -- advanced once per plane
+    uint32_t sprev = rs, scur = rs + 1 == MG_NST ? 0 : rs + 1, pcur = rs + 1 == MG_NST ? rp ^ 1 : rp;
     {
-      const uint32_t q0 = seq % MG_NST, q1 = (seq + 1) % MG_NST;
-      mbar_wait(&full[q0], (seq / MG_NST) & 1);
-      const float* lo = reinterpret_cast<const float*>(tiles + q0 * MG_STAGE_STRIDE) + coff;
+      mbar_wait(&full[sprev], rp);
+      const float* lo = reinterpret_cast<const float*>(tiles + sprev * MG_STAGE_STRIDE) + coff;
       lt = *reinterpret_cast<const float2*>(lo);
       lb = *reinterpret_cast<const float2*>(lo + MG_BOXW);
-      mbar_wait(&full[q1], ((seq + 1) / MG_NST) & 1);
-      const float* c0 = reinterpret_cast<const float*>(tiles + q1 * MG_STAGE_STRIDE) + coff;
+      mbar_wait(&full[scur], pcur);
+      const float* c0 = reinterpret_cast<const float*>(tiles + scur * MG_STAGE_STRIDE) + coff;
       pt = *reinterpret_cast<const float2*>(c0);
       pb = *reinterpret_cast<const float2*>(c0 + MG_BOXW);
       const unsigned ca = cn0 & 0xffu, cb = cn0 >> 8, cc = cn1 & 0xffu, cd = cn1 >> 8;
@@ -487,15 +494,17 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
     for (int k = 1; k <= len; k++) {
       const int lz = zb + k - 1;
       __syncthreads();  // every thread is done with plane k-1's stage
-      if (tid == 0 && k - 1 + MG_NST < nplanes) {
-        const uint32_t st = (seq + k - 1) % MG_NST;
-        mbar_expect_tx(&full[st], MG_STAGE_BYTES);
-        tma_load_3d(tiles + st * MG_STAGE_STRIDE, &tm, &full[st], xo - MG_HX, yo - 1, zb + k - 1 + MG_NST);
+      if (tid == 0 && k - 1 + MG_NST < nplanes) {  // the stage of plane k-1 takes plane k-1+NST
+        mbar_expect_tx(&full[sprev], MG_STAGE_BYTES);
+        tma_load_3d(tiles + sprev * MG_STAGE_STRIDE, &tm, &full[sprev], xo - MG_HX, yo - 1, zb + k - 1 + MG_NST);
       }
-      const uint32_t scs = (seq + k) % MG_NST, sn = (seq + k + 1) % MG_NST;
-      mbar_wait(&full[sn], ((seq + k + 1) / MG_NST) & 1);
-      const float* cur = reinterpret_cast<const float*>(tiles + scs * MG_STAGE_STRIDE) + coff;
+      const uint32_t sn = scur + 1 == MG_NST ? 0 : scur + 1, pn_ = scur + 1 == MG_NST ? pcur ^ 1 : pcur;
+      mbar_wait(&full[sn], pn_);
+      const float* cur = reinterpret_cast<const float*>(tiles + scur * MG_STAGE_STRIDE) + coff;
       const float* nxt = reinterpret_cast<const float*>(tiles + sn * MG_STAGE_STRIDE) + coff;
+      sprev = scur;
+      scur = sn;
+      pcur = pn_;
       const float2 nt0 = *reinterpret_cast<const float2*>(nxt), nb0 = *reinterpret_cast<const float2*>(nxt + MG_BOXW);
       float2 ut = nt0, ub = nb0;
       const unsigned k0 = cn0, k1 = cn1;
@@ -624,7 +633,8 @@ __global__ void __launch_bounds__(NTHR, 3) k_mg_fine(const __grid_constant__ CUt
       ci += plane;
       cu += pplane;
     }
-    seq += nplanes;
+    rs = scur + 1 == MG_NST ? 0 : scur + 1;  // scur: the plane above the chunk, the item's last
+    rp = scur + 1 == MG_NST ? pcur ^ 1 : pcur;
     if (push && (zb == 0 || zb + len == D.nz)) halo_signal(H, zb == 0, zb + len == D.nz);
   }
   if (OUT == 2) {

@@ -106,6 +106,51 @@ static int ensure_ws(const Dom& D) {
   return 0;
 }
 
+// ---- phase trace (KEFFB200_TRACE=k: CUDA events around the phases of iteration k of the grid solver, printed to
+// stderr at the end of the solve; 0 / unset = off).  Diagnostic only: an event per phase, nothing else changes.
+struct Trace {
+  int want = -1;        // iteration to trace (-1 = off)
+  bool live = false;    // marks are being recorded right now
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> name;
+};
+static Trace& trace() {
+  static thread_local Trace t;
+  static const int want = getenv("KEFFB200_TRACE") ? atoi(getenv("KEFFB200_TRACE")) : -1;
+  t.want = want;
+  return t;
+}
+static void trace_mark(const char* what) {
+  Trace& t = trace();
+  if (!t.live) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx().st);
+  t.ev.push_back(e);
+  t.name.push_back(what);
+}
+static void trace_report(int rank) {
+  Trace& t = trace();
+  if (t.ev.size() < 2) return;
+  cudaEventSynchronize(t.ev.back());
+  std::string line = "[keffb200 trace] rank " + std::to_string(rank) + " iteration " + std::to_string(t.want) + ":";
+  float total = 0;
+  for (size_t i = 1; i < t.ev.size(); i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.ev[i - 1], t.ev[i]);
+    total += ms;
+    char b[96];
+    snprintf(b, sizeof b, " %s %.0f", t.name[i], ms * 1e3);
+    line += b;
+  }
+  char b[64];
+  snprintf(b, sizeof b, " | total %.0f us", total * 1e3);
+  fprintf(stderr, "%s%s\n", line.c_str(), b);
+  for (cudaEvent_t e : t.ev) cudaEventDestroy(e);
+  t.ev.clear();
+  t.name.clear();
+}
+
 // ---- NCCL helpers (no-ops when world == 1) -----------------------------------------------------
 static int nccl_check(int rc, const char* what) {
   if (rc == 0) return 0;
@@ -742,8 +787,14 @@ static int mg_fine_pass(const Mg& mg, int in, int out, bool add_e, const MgPass&
   float* fout = out >= 0 ? c.xf[out] + uplane : nullptr;
   Fused f;
   if (out >= 0) f = fused_push(out == 0 ? HF_XF0 : HF_XF1, out == 0 ? W_XF0 : W_XF1, uplane * sizeof(float), mg.D.nz);
+  MgCoefF cf;
+  for (int d = 0; d < 3; d++) {
+    cf.same[d][0] = (float)mg.C.same[d][0];
+    cf.same[d][1] = (float)mg.C.same[d][1];
+    cf.diff[d] = (float)mg.C.diff[d];
+  }
 #define KB_FINE(O, E, U) \
-  k_mg_fine<O, E, U><<<mg.grid, NTHR, 0, c.st>>>(tm, c.code, c.mg_tab, uown, fout, z, mf, K, mg.C, mg.D, mg.plan, c.S, c.partials, f.H)
+  k_mg_fine<O, E, U><<<mg.grid, NTHR, 0, c.st>>>(tm, c.code, c.mg_tab, uown, fout, z, mf, K, cf, mg.D, mg.plan, c.S, c.partials, f.H)
   const bool isu = in == 0;
   if (out == -1) {
     if (isu) KB_FINE(0, 0, 1); else KB_FINE(0, 0, 0);
@@ -785,7 +836,9 @@ static int mg_vcycle(const Mg& mg, float* z) {
     cur = out + 1;
     sc = 1.f;
   }
+  trace_mark("fineA+wait");
   KB_TRY(mg_fine_pass(mg, cur, -1, false, MgPass{sc, -1.f, 1.f, 1.f}, z));
+  trace_mark("fineB");
   const int fine_cur = cur;
   const float fine_sc = sc;
   // ---- stored levels, down ----
@@ -827,6 +880,7 @@ static int mg_vcycle(const Mg& mg, float* z) {
     lcur[l] = in;
     lsc[l] = s1;
   }
+  trace_mark("levels-down");
   // ---- dense level (replicated; its u array holds the plain right-hand side) ----
   {
     const MgLevel& L = mg.L[mg.nlev];
@@ -869,12 +923,14 @@ static int mg_vcycle(const Mg& mg, float* z) {
       s1 = 1.f;
     }
   }
+  trace_mark("dense+levels-up");
   // ---- voxel grid, up ----
   cur = fine_cur;
   sc = fine_sc;
   for (int k = nu0 - 1; k >= 0; k--) {
     const int out = k == 0 ? -2 : (cur == 1 ? 1 : 0);
     KB_TRY(mg_fine_pass(mg, cur, out, k == nu0 - 1, MgPass{sc, 1.f - w0[k], w0[k], w0[k]}, z));
+    trace_mark(k == 0 ? "fineD" : "fineC+wait");
     cur = out + 1;
     sc = 1.f;
   }
@@ -968,25 +1024,36 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   // iteration k since the last (re)start; every kernel returns at once when the stop flag is up
   auto enqueue_iter = [&](long k) -> int {
     const int par = (int)(k & 1);
+    trace().live = trace().want >= 0 && k == trace().want && trace().ev.empty();
+    trace_mark("start");
     if (!p_pushed) KB_TRY(exchange_halo(c.p, D, c.st, pesz));
     KB_TRY(stencil_launch<MODE_APPLY>(s, p32 ? 2 : 1, q, nullptr));
+    trace_mark("stencil");
     KB_TRY(reduce_step<RS_PQ>(s.grid, 0));
+    trace_mark("allreduce-pq");
     if (mg.on) {
       const Fused fu = fused_push(HF_U, W_U, (size_t)mg.pitch * D.ny * sizeof(float), D.nz);
       k_cg_update_mg<1><<<mg.gu, vt, 0, c.st>>>(r, q, c.code, c.mg_tab, c.u + (size_t)mg.pitch * D.ny, mg.pitch, D, c.S, par,
                                                 c.partials, fu.H);
       KB_LAUNCHED();
       mg.u_pushed = fu.on;
+      trace_mark("update");
       KB_TRY(reduce_step<RS_RR_MG>(mg.gu, 0));
+      trace_mark("allreduce-rr");
       KB_TRY(fused_wait(fu, (unsigned)mg.gu));
+      trace_mark("wait-u");
       KB_TRY(mg_vcycle(mg, c.z));
       KB_TRY(reduce_step<RS_RZ_MG>(mg.grid, par ^ 1));
+      trace_mark("allreduce-rz");
       const Fused fp = fused_push(HF_P, W_P, plane * pesz, D.nz);
       if (p32) k_cg_dir_mg<float><<<gm, 256, 0, c.st>>>(x, pf, c.z, n2, (long)n, c.S, par, (long long)k, 0, fp.H, (long)(plane / 2));
       else k_cg_dir_mg<double><<<gm, 256, 0, c.st>>>(x, p, c.z, n2, (long)n, c.S, par, (long long)k, 0, fp.H, (long)(plane / 2));
       KB_LAUNCHED();
       p_pushed = fp.on;
+      trace_mark("dir");
       KB_TRY(fused_wait(fp, (unsigned)gm));
+      trace_mark("wait-p");
+      trace().live = false;
       return 0;
     }
     if (V == 2) k_cg_update<2><<<gv, vt, 0, c.st>>>(x, r, p, q, c.code, C, D, c.S, par, c.partials);
@@ -1087,6 +1154,8 @@ static int solve_grid(const uint8_t* d_mask_halo, const Dom& D, const keffb200_p
   KB_CUDA(cudaStreamSynchronize(c.st));
   float ms = 0;
   KB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  trace().live = false;
+  trace_report(c.dist_active ? (c.link.p2p ? c.link.rank : c.nccl.rank) : 0);
   if (out) {
     out->keff = keff;
     out->q_left = ql;
