@@ -490,8 +490,17 @@ def main():
         # (1) slab-vs-single parity on the record: a 256^3 splitmix volume in `world` slabs against rank 0 alone
         npar = 256
         rp, z0p, nzlp = slab_case(npar, npar, want_T=True)
+        # Device-wide sync before the field leaves: without it the 8-GPU run of this leg twice delivered rank 0's slab as
+        # stale memory (Keff, computed inside the solve, was right; the other seven slabs too), while the stand-alone
+        # replay of the same sequence (scratch/dbg_slabT.py) never did -- an ordering hazard between the NCCL stream of
+        # the gather and the generator / allocator traffic of this script, not of the solve.  The sums make it checkable.
+        torch.cuda.synchronize()
+        sum_before = float(rp["T"].sum().item())                    # each rank's own field before it travels
         parts = [torch.empty_like(rp["T"]) for _ in range(world)]
         dist.all_gather(parts, rp["T"])
+        torch.cuda.synchronize()
+        sums = [None] * world
+        dist.all_gather_object(sums, (sum_before, float(rp["T"].sum().item()), float(parts[rank].sum().item())))
         if rank == 0:
             full = api.bernoulli_volume_dev((npar, npar, npar), 0.5, 1234, device=local)
             s1 = api.solve3d(full, ps, device=local)
@@ -505,6 +514,7 @@ def main():
                                   "iters_slab": rp["iters"], "iters_single": s1["iters"], "status": rp["status"]}
             if max(per_slab) > 1e-6:                                # diagnostics for the record: which field is off, and how
                 out["slab_parity"]["diagnostic"] = {
+                    "own_field_sums_before_gather_after_gather_own_part": sums,
                     "single_T_range": [float(s1["T"].min().item()), float(s1["T"].max().item())],
                     "single_T_zeros": int((s1["T"] == 0).sum().item()),
                     "slab_T_ranges": [[float(q.min().item()), float(q.max().item())] for q in parts],

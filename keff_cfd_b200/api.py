@@ -270,5 +270,8 @@ def bernoulli_volume_dev(shape, p=0.5, seed=1234, z0=0, device=None):
     device = _lib.ensure(device)
     nz, ny, nx = shape
     out = torch.empty(shape, dtype=torch.uint8, device=f"cuda:{device}")
+    # the caching allocator may hand back a block whose previous owner still has work queued on torch's stream:
+    # the library's stream must run behind it before it writes the block
+    _lib.order_after_torch(out)
     check(lib().keffb200_gen_bernoulli_dev(out.data_ptr(), nz * ny * nx, z0 * ny * nx, seed, p))
     return out
