@@ -145,7 +145,10 @@ static void trace_report(int rank) {
   }
   char b[64];
   snprintf(b, sizeof b, " | total %.0f us", total * 1e3);
-  fprintf(stderr, "%s%s\n", line.c_str(), b);
+  line += b;
+  line += "\n";
+  if (write(2, line.data(), line.size()) < 0) {  // one write: lines of several ranks must not interleave
+  }
   for (cudaEvent_t e : t.ev) cudaEventDestroy(e);
   t.ev.clear();
   t.name.clear();
