@@ -59,3 +59,34 @@ def test_multigrid_high_contrast_and_other_walls(K):
         b = K.solve3d(m, K.default_params(rel_residual=1e-10, flags=K.F_NO_MG, **kw))
         assert a["status"] == 0 and abs(a["keff"] - b["keff"]) <= 1e-8 * abs(b["keff"])
         assert a["iters"] < b["iters"]
+
+
+def test_fp32_search_direction_lands_on_the_same_solution(K):
+    """The multigrid path stores p in FP32 (x and r advance with the same stored p, so r stays the residual of x);
+    KEFFB200_P64=1 keeps it in FP64.  Same iteration count, same field to solver tolerance -- and the stencil bench
+    entry point accepts the FP32-input form the iteration launches."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    prog = ("import json, sys, numpy as np; sys.path.insert(0, %r); import keff_cfd_b200 as K; "
+            "from keff_cfd_b200 import structures as S; K.init(0); "
+            "m = S.bernoulli_volume((40, 48, 64), 0.5, 21); r = K.solve3d(m, K.default_params(rel_residual=1e-11)); "
+            "print(json.dumps({'keff': r['keff'], 'iters': r['iters'], 'status': r['status'], "
+            "'T': [float(r['T'].min()), float(r['T'].max()), float(np.abs(r['T']).sum())]}))" % ROOT)
+    out = {}
+    for tag, env in (("p32", {}), ("p64", {"KEFFB200_P64": "1"})):
+        r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env={**os.environ, **env}, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        out[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    a, b = out["p32"], out["p64"]
+    assert a["status"] == 0 and b["status"] == 0 and abs(a["iters"] - b["iters"]) <= 1
+    assert abs(a["keff"] - b["keff"]) <= 1e-10 * abs(b["keff"])
+    assert abs(a["T"][2] - b["T"][2]) <= 1e-9 * b["T"][2]
+    import torch
+    from keff_cfd_b200 import api
+    vol = api.bernoulli_volume_dev((64, 64, 128), 0.5, 5)
+    assert api.bench_apply(vol, api.default_params(flags=32), reps=3) > 0
+    with pytest.raises(Exception):
+        api.bench_apply(api.bernoulli_volume_dev((16, 16, 18), 0.5, 5), api.default_params(flags=32), reps=1)   # nx % 4 != 0
