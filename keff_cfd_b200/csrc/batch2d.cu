@@ -197,18 +197,29 @@ __global__ void __launch_bounds__(1024, 1)
 // Enqueue the solve of images [first, first+count) of a device-resident batch on the compute stream
 // (asynchronous).  Result records go to the device array slot of each image; counters[slot] is the
 // work counter of this launch.
+static bool batch2d_onchip_shape(int nx, int ny, const keffb200_params& P) {
+  return !(P.flags & KEFFB200_F_BATCH_GLOBAL) && nx <= 128 && nx % 4 == 0 && ny <= 128 && ny % 8 == 0;
+}
+// on-chip multigrid kernel: sides multiples of 16 (four 2x coarsenings down to the dense level)
+static bool batch2d_uses_mg(int nx, int ny, const keffb200_params& P) {
+  static const bool no_mgk = getenv("KEFFB200_BATCH_NO_MG") != nullptr;
+  return batch2d_onchip_shape(nx, ny, P) && !no_mgk && !(P.flags & KEFFB200_F_BATCH_ADDITIVE) && nx % 16 == 0 && ny % 16 == 0 &&
+         nx >= 16 && ny >= 16;
+}
+
+// ready (nullable, multigrid kernel only): device counter of the images already resident (see batch2d_solve_host)
 static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx, int ny, const keffb200_params& P,
-                           double* d_T_out, double* ws, uint8_t* codes, BatchOut* res, int* counters, int slot) {
+                           double* d_T_out, double* ws, uint8_t* codes, BatchOut* res, int* counters, int slot,
+                           const unsigned int* ready = nullptr) {
   Ctx& c = ctx();
   const size_t n = (size_t)nx * ny;
   const int grid = std::min(count, c.sms);
   const Coef C = make_coef(nx, ny, 1, P);
-  const bool onchip = !(P.flags & KEFFB200_F_BATCH_GLOBAL) && nx <= 128 && nx % 4 == 0 && ny <= 128 && ny % 8 == 0;
+  const bool onchip = batch2d_onchip_shape(nx, ny, P);
   const uint8_t* m = d_solid + (size_t)first * n;
   double* T = d_T_out ? d_T_out + (size_t)first * n : nullptr;
-  // on-chip multigrid kernel: sides multiples of 16 (four 2x coarsenings down to the dense level)
-  static const bool no_mgk = getenv("KEFFB200_BATCH_NO_MG") != nullptr;
-  const bool mgk = onchip && !no_mgk && !(P.flags & KEFFB200_F_BATCH_ADDITIVE) && nx % 16 == 0 && ny % 16 == 0 && nx >= 16 && ny >= 16;
+  const bool mgk = batch2d_uses_mg(nx, ny, P);
+  if (ready && !mgk) return fail(KEFFB200_ESTATE, "streamed batches need the on-chip multigrid kernel");
   if (onchip) {
     CoefF F;
     for (int ph = 0; ph < 2; ph++) {
@@ -235,7 +246,7 @@ static int batch2d_enqueue(const uint8_t* d_solid, int first, int count, int nx,
       static const double delta2 = getenv("KEFFB200_BATCH_DELTA") ? atof(getenv("KEFFB200_BATCH_DELTA")) : 1e-4;
       k_batch2d_mg<<<grid, MB_THREADS, MB_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual, P.flux_balance,
                                                         (long long)P.max_iter, (P.flags & KEFFB200_F_ZERO_INIT) ? 1 : 0, om, wc1, wc2, delta2,
-                                                        ws, T, res + first, counters + slot);
+                                                        ws, T, res + first, counters + slot, ready);
     } else
     k_batch2d_onchip<<<grid, OC_THREADS, OC_SMEM, c.st>>>(m, count, nx, ny, C, F, P.rel_residual * P.rel_residual,
                                                           P.flux_balance, (long long)P.max_iter,
@@ -357,9 +368,13 @@ int batch2d_solve_dev(const uint8_t* d_solid, int n_img, int nx, int ny, const k
   return batch2d_rescue(d_solid, n_img, nx, ny, P, d_T_out, w, out);
 }
 
-// Host structures: the H2D copy runs on a second stream in three pieces (1/16, 3/16, 3/4 of the batch)
-// and each piece's solve waits only for its own copy, so all but the first 1/8 of the transfer hides
-// behind compute.  d_stage: device staging buffer for the whole batch.
+// Host structures.  On-chip multigrid kernel: ONE launch over the whole batch is enqueued first and the structures
+// stream in behind it on a second stream, chunk by chunk, each chunk followed by a 4-byte copy that publishes how many
+// images are resident; a CTA that draws an image which has not arrived yet waits on that counter.  Only the first
+// chunk (1/32 of the batch) is exposed, there is one kernel tail instead of one per piece, and a caller with pageable
+// memory -- whose cudaMemcpyAsync blocks the host chunk by chunk -- still overlaps its copy with the solve.
+// Other kernels: three pieces (1/16, 3/16, 3/4), each piece's launch waits only for its own copy.
+// d_stage: device staging buffer for the whole batch.
 int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int nx, int ny, const keffb200_params& P,
                        double* d_T_out, keffb200_result* out) {
   Ctx& c = ctx();
@@ -367,14 +382,32 @@ int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int 
   BatchWs w;
   KB_TRY(batch2d_workspace(n_img, nx, ny, w));
   const size_t n = (size_t)nx * ny;
+  KB_CUDA(cudaEventRecord(c.ev0, c.st));
+  KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
+  KB_CUDA(cudaEventRecord(c.evx, c.st));
+  KB_CUDA(cudaStreamWaitEvent(c.st2, c.evx, 0));  // staging buffer free (previous call's kernels are done), counters zeroed
+  // experiments: KEFFB200_BATCH_PIECES keeps the three-piece scheme; a launch that is synchronised at once
+  // (KEFFB200_DEBUG_SYNC) must not wait for copies that are enqueued after it
+  static const bool no_stream = getenv("KEFFB200_BATCH_PIECES") != nullptr || getenv("KEFFB200_DEBUG_SYNC") != nullptr;
+  if (batch2d_uses_mg(nx, ny, P) && c.h_ready && !no_stream) {
+    unsigned int* ready = reinterpret_cast<unsigned int*>(w.counters + 8);
+    KB_TRY(batch2d_enqueue(d_stage, 0, n_img, nx, ny, P, d_T_out, w.ws, w.codes, w.res, w.counters, 0, ready));
+    const int nchunk = std::max(1, std::min(KB_READY_SLOTS, n_img / std::max(1, c.sms)));
+    for (int k = 0; k < nchunk; k++) {
+      const int first = (int)((long long)n_img * k / nchunk), last = (int)((long long)n_img * (k + 1) / nchunk);
+      if (last <= first) continue;
+      KB_CUDA(cudaMemcpyAsync(d_stage + (size_t)first * n, h_solid + (size_t)first * n, (size_t)(last - first) * n,
+                              cudaMemcpyHostToDevice, c.st2));
+      c.h_ready[k] = (unsigned int)last;
+      KB_CUDA(cudaMemcpyAsync(ready, &c.h_ready[k], sizeof(unsigned int), cudaMemcpyHostToDevice, c.st2));
+    }
+    KB_TRY(batch2d_collect(w, n_img, P, out));
+    return batch2d_rescue(d_stage, n_img, nx, ny, P, d_T_out, w, out);
+  }
   // pieces of 1/16, 3/16 and 3/4 of the batch: only the first copy (1/16) is exposed, and every later copy is
   // shorter than the compute it hides behind (a 128x128 image takes ~6x longer to solve than to copy)
   int cut[4] = {0, n_img / 16, n_img / 4, n_img};
   if (n_img < 8 * c.sms) cut[1] = cut[2] = 0;  // small batches: one piece
-  KB_CUDA(cudaEventRecord(c.ev0, c.st));
-  KB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), c.st));
-  KB_CUDA(cudaEventRecord(c.evx, c.st));
-  KB_CUDA(cudaStreamWaitEvent(c.st2, c.evx, 0));  // staging buffer free (previous call's kernels are done)
   for (int k = 0; k < 3; k++) {
     const int first = cut[k], count = cut[k + 1] - cut[k];
     if (count <= 0) continue;

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
     k_batch2d_mg(const uint8_t* __restrict__ masks, int n_img, int nx, int ny, const Coef C, const CoefF F, double thr2_in,
                  double flux_tol, long long max_iter, int const_init, float om, float wc1, float wc2, double delta2,
                  double* __restrict__ xws,
-                 double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter) {
+                 double* __restrict__ T_out, BatchOut* __restrict__ res, int* counter, const unsigned int* ready) {
   extern __shared__ __align__(16) unsigned char mb_smem[];
   float* SM = reinterpret_cast<float*>(mb_smem);
   float* P = SM + MB_F_P;
@@ -353,7 +353,13 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   const int o1 = ((y0 >> 1) + 1) * p1 + 2 + (x0 >> 1);
 
   while (true) {
-    if (tid == 0) *s_img = atomicAdd(counter, 1);
+    if (tid == 0) {
+      int i = atomicAdd(counter, 1);
+      // host batches stream in while the kernel runs: `ready` counts the images whose structure has landed in HBM
+      // (written by the copy stream behind each chunk); images are taken in copy order
+      if (ready && i < n_img && !wait_counter(ready, (unsigned)i + 1u)) i = n_img;
+      *s_img = i;
+    }
     __syncthreads();
     const int img = *s_img;
     __syncthreads();

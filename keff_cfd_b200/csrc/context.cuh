@@ -71,6 +71,8 @@ struct Link {
   WinTable* h_win = nullptr;  // pinned staging of window tables
 };
 
+constexpr int KB_READY_SLOTS = 32;  // chunks of a streamed host batch
+
 struct Ctx {
   bool ready = false;
   int device = -1, sms = 0;
@@ -110,6 +112,7 @@ struct Ctx {
   bool dist_active = false;  // true only inside a slab solve: halo exchange + all-reduces enabled
   // scalar records of the last two convergence checks (pinned): the host reads check k while check k+1 is queued
   Scal* hring = nullptr;
+  unsigned int* h_ready = nullptr;  // page-locked: image counts published behind the chunks of a streamed host batch
   cudaEvent_t evb[2] = {nullptr, nullptr};
   // per-device function attributes already applied (dynamic shared memory sizes)
   bool attr_batch = false, attr_ws = false;

@@ -1262,6 +1262,7 @@ static int init_context(Ctx& c, int device) {
   KB_CUDA(cudaMemset(c.S, 0, sizeof(Scal)));
   KB_CUDA(cudaMallocHost(&c.hS, sizeof(Scal)));
   KB_CUDA(cudaMallocHost(&c.hring, 2 * sizeof(Scal)));
+  KB_CUDA(cudaMallocHost(&c.h_ready, KB_READY_SLOTS * sizeof(unsigned int)));
   for (int k = 0; k < 2; k++) KB_CUDA(cudaEventCreateWithFlags(&c.evb[k], cudaEventDisableTiming));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qr;
@@ -1314,6 +1315,8 @@ static void destroy_context(Ctx& c) {
   if (c.hS) cudaFreeHost(c.hS);
   if (c.hring) cudaFreeHost(c.hring);
   c.hring = nullptr;
+  if (c.h_ready) cudaFreeHost(c.h_ready);
+  c.h_ready = nullptr;
   for (int k = 0; k < 2; k++) {
     if (c.evb[k]) cudaEventDestroy(c.evb[k]);
     c.evb[k] = nullptr;
