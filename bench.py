@@ -359,7 +359,9 @@ def main():
                 "ms_per_step": 1e3 * dt_e / args.steps, "wall_ms_per_step": 1e3 * wall_e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"kernel": "k_batch2d_mg", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_batch2d_mg", n_img), "peak_kind": peak_kind,
+                     "frac": achieved / peak, "frac_kind": "HBM-equivalent work rate (SURVEY 8d: 16 B x cell-updates), NOT DRAM "
+                     "bandwidth: see hbm_true for the DRAM fraction and issue for the bound that applies",
+                     "traffic": ncu_traffic("k_batch2d_mg", n_img), "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": 16.0 * updates_per_step,
                      "note": "HBM-equivalent: 16 B x cell-updates / kernel time (4.31 stencil passes per CG iteration, see "
                              "DESIGN 3).  The whole solve of an image runs inside one SM (shared memory, registers, an "
