@@ -301,6 +301,9 @@ static int batch2d_collect(const BatchWs& w, int n_img, const keffb200_params& P
   KB_CUDA(cudaStreamSynchronize(c.st));
   float ms = 0;
   KB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+  for (int i = 0; i < n_img; i++)
+    if (h[i].status == -1 && h[i].pad == -1)
+      return fail(KEFFB200_ECUDA, "image %d was never solved: its structure did not reach the GPU (host copy failed or stalled)", i);
   for (int i = 0; i < n_img; i++) {
     keffb200_result& o = out[i];
     o.q_left = h[i].ql;
@@ -391,6 +394,8 @@ int batch2d_solve_host(const uint8_t* h_solid, uint8_t* d_stage, int n_img, int 
   static const bool no_stream = getenv("KEFFB200_BATCH_PIECES") != nullptr || getenv("KEFFB200_DEBUG_SYNC") != nullptr;
   if (batch2d_uses_mg(nx, ny, P) && c.h_ready && !no_stream) {
     unsigned int* ready = reinterpret_cast<unsigned int*>(w.counters + 8);
+    // a record that keeps this pattern was never written: its image did not arrive within the kernel's wait limit
+    KB_CUDA(cudaMemsetAsync(w.res, 0xff, (size_t)n_img * sizeof(BatchOut), c.st));
     KB_TRY(batch2d_enqueue(d_stage, 0, n_img, nx, ny, P, d_T_out, w.ws, w.codes, w.res, w.counters, 0, ready));
     const int nchunk = std::max(1, std::min(KB_READY_SLOTS, n_img / std::max(1, c.sms)));
     for (int k = 0; k < nchunk; k++) {
