@@ -118,6 +118,13 @@ __device__ __forceinline__ void mb_north_d(unsigned c, const Coef& C, bool top, 
     n[i] = top ? 0.0 : ((c & (C_N << (8 * i))) ? C.diff[1] : ((c & (C_PH << (8 * i))) ? C.same[1][1] : C.same[1][0]));
 }
 
+// idx / d for 0 <= idx <= 4096, 2 <= d <= 64 without a division: the high word of idx * (floor(2^32 / d) + 1)
+// (exact on that range; checked exhaustively).  mb_rcp(d) is computed once per launch; 0 stands for d = 1.
+__device__ __forceinline__ unsigned mb_rcp(int d) {
+  return d <= 1 ? 0u : 0xffffffffu / (unsigned)d + ((0xffffffffu % (unsigned)d) + 1u == (unsigned)d ? 2u : 1u);
+}
+__device__ __forceinline__ int mb_div(int idx, unsigned rcp) { return rcp ? (int)__umulhi((unsigned)idx, rcp) : idx; }
+
 // ---- coarse levels (shared-memory arrays with a zero guard ring: cell (X,Y) at (Y+1)*pitch + 2 + X) ----
 template <int L>
 struct MbLv {
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   double* SC = bc + 4;  // block-uniform FP64 scalars that are only looked at around reliable updates (every thread
                         // writes the same value, and only plain assignments -- never read-modify-write): parked here so that they do not occupy registers in the passes
   int* s_img = reinterpret_cast<int*>(SC + 16);
+  unsigned* s_rcp = reinterpret_cast<unsigned*>(s_img + 4);  // reciprocal for r / nax (mb_div) in the dense-level product
 
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int x0 = lane * 4, y0 = wrp * 8;
@@ -336,6 +344,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
   const float om1 = 1.f - om;
 
   for (int i = tid; i < MB_F_END; i += MB_THREADS) SM[i] = 0.f;  // guard rings stay zero for the whole launch
+  if (tid == 0) s_rcp[0] = mb_rcp(nax);
   float* Uown = P + (y0 + 1) * MB_PITCH + x0;  // my patch's first row inside the guarded image of u
   // y and z slices: thread-major float4 rows at compile-time offsets from one base
   float4* Yg = reinterpret_cast<float4*>(xws + (size_t)blockIdx.x * mb_ws_stride(n)) + tid;
@@ -576,22 +585,22 @@ __global__ void __launch_bounds__(MB_THREADS, 1)
       __syncthreads();
       mb_restrict<3>(LV, X3, B4, nx3, ny3, tid);
       __syncthreads();
-      {  // dense level: e4 = inverse * b4; 8 threads per row
+      {  // dense level: e4 = inverse * b4; 8 threads per row, 8 columns each (columns >= na of the inverse and entries
+         // >= na of b4 are zero: no bounds inside the product)
         const int r = tid >> 3, part = tid & 7;
-        float s = 0.f;
-        if (r < na) {
+        float sum = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const int c = part * 8 + k;
-            if (c < na) s += AI[r * MB_NA + c] * B4[c];
-          }
+        for (int h = 0; h < 2; h++) {
+          const float4 av = *reinterpret_cast<const float4*>(AI + r * MB_NA + part * 8 + 4 * h);
+          const float4 bv = *reinterpret_cast<const float4*>(B4 + part * 8 + 4 * h);
+          sum += (av.x * bv.x + av.y * bv.y) + (av.z * bv.z + av.w * bv.w);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
         if (part == 0 && r < na) {
-          const int by = r / nax, ax = r - by * nax;
-          E4[(by + 1) * mb_pitch(4) + 2 + ax] = s;
+          const int by = mb_div(r, s_rcp[0]), ax = r - by * nax;
+          E4[(by + 1) * mb_pitch(4) + 2 + ax] = sum;
         }
       }
       __syncthreads();
