@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_mg_sweep(const MgLevelView L, const flo
 // x += P e: the correction of the next level added to a stored iterate in place (planes z_first .. z_last: the
 // z-halo planes of the iterate take the correction of the neighbour's aggregates from the halo planes of e).
 // The sweep that follows is then a plain one: adding P e on the fly costs it seven more loads per cell (measured
-// at 256^3: 281 us against 118 us for the plain sweep; this pass moves 8.5 B per cell, 40 us).
+// at 256^3: 281 us against 118 us for the plain sweep; this pass moves 8.5 B per cell and takes 68 us).
 __global__ void __launch_bounds__(256) k_mg_prolong_add(int nx, int ny, int z_first, int z_last, float* __restrict__ x,
                                                         const float* __restrict__ ec, int fx, int fy, int fz, int cnx,
                                                         int cny, int bx, const Scal* __restrict__ S) {
