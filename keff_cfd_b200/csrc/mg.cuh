@@ -247,11 +247,28 @@ __global__ void __launch_bounds__(256) k_mg_prolong_add(int nx, int ny, int z_fi
   if (S->done) return;
   const int plane = nx * ny, cplane = cnx * cny;
   const int tx = threadIdx.x & (bx - 1), trow = threadIdx.x / bx, rpb = blockDim.x / bx;
+  // four cells = two aggregates per thread when rows allow it (x coarsened, nx a multiple of 4: rows of both arrays
+  // are then 16 / 8 byte aligned -- level arrays start on 128-byte boundaries and their planes are multiples of 4)
+  const bool vec = fx && (nx & 3) == 0 && (cnx & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(ec) & 7)) == 0;
   for (int z = z_first + (int)blockIdx.y; z <= z_last; z += gridDim.y)
   for (int y = blockIdx.x * rpb + trow; y < ny; y += gridDim.x * rpb) {
     const float* er = ec + (fz ? z >> 1 : z) * cplane + (fy ? y >> 1 : y) * cnx;
     float* xr = x + z * plane + y * nx;
-    for (int xx = tx; xx < nx; xx += bx) xr[xx] += er[fx ? xx >> 1 : xx];
+    if (vec) {
+      float4* xr4 = reinterpret_cast<float4*>(xr);
+      const float2* er2 = reinterpret_cast<const float2*>(er);
+      for (int q = tx; q < (nx >> 2); q += bx) {
+        float4 v = xr4[q];
+        const float2 e = er2[q];
+        v.x += e.x;
+        v.y += e.x;
+        v.z += e.y;
+        v.w += e.y;
+        xr4[q] = v;
+      }
+    } else {
+      for (int xx = tx; xx < nx; xx += bx) xr[xx] += er[fx ? xx >> 1 : xx];
+    }
   }
 }
 

@@ -908,9 +908,10 @@ static int mg_vcycle(const Mg& mg, float* z) {
         // the iterate is a stored array of its own (nu >= 2): add P e to it in place (halo planes included), then sweep
         float* xin = in == L.t0 ? L.t0 : L.t1;
         const int zf = llo ? -1 : 0, zl = L.nz - 1 + (lhi ? 1 : 0);
-        dim3 gp = gl;
-        gp.y = (unsigned)std::max(1, std::min<int>(zl - zf + 1, (int)gl.y));
-        k_mg_prolong_add<<<gp, 256, 0, c.st>>>(L.nx, L.ny, zf, zl, xin, N.e + on, L.fx, L.fy, L.fz, N.nx, N.ny, mg_bx(L.nx), c.S);
+        // (four cells per thread along x where rows allow it: the block shape follows nx / 4)
+        const int pnx = (L.fx && L.nx % 4 == 0) ? L.nx / 4 : L.nx;
+        dim3 gp = mg_row_grid(pnx, L.ny, zl - zf + 1);
+        k_mg_prolong_add<<<gp, 256, 0, c.st>>>(L.nx, L.ny, zf, zl, xin, N.e + on, L.fx, L.fy, L.fz, N.nx, N.ny, mg_bx(pnx), c.S);
         KB_LAUNCHED();
         k_mg_sweep<0><<<gl, 256, 0, c.st>>>(mg_view(L), in, L.u, nullptr, K, L.fx, L.fy, L.fz, N.nx, N.ny, out, llo, lhi,
                                             mg_bx(L.nx), c.S);
