@@ -130,10 +130,13 @@ static inline int extend(int v, int t) { return t && v < (1 << (t - 1)) ? v - (1
 // 1-D LL&M inverse DCT on eight values, constants scaled by 2^12 (IJG jidctint "islow"); out[k], out[7-k] = e[k] +- o[k]
 static inline void llm_1d(const int* s, int stride, int (&e)[4], int (&o)[4]) {
   constexpr int F = 4096;
-  auto fx = [](double x) { return (int)(x * F + 0.5); };
-  static const int c0541 = fx(0.5411961f), c1847 = fx(-1.847759065f), c0765 = fx(0.765366865f), c1175 = fx(1.175875602f);
-  static const int c0298 = fx(0.298631336f), c2053 = fx(2.053119869f), c3072 = fx(3.072711026f), c1501 = fx(1.501321110f);
-  static const int c0899 = fx(-0.899976223f), c2562 = fx(-2.562915447f), c1961 = fx(-1.961570560f), c0390 = fx(-0.390180644f);
+  // (int)(c * 4096 + 0.5) of the single-precision constant, truncating -- the reference decoder's rounding of them
+  constexpr int c0541 = (int)((double)0.5411961f * F + 0.5), c1847 = (int)((double)-1.847759065f * F + 0.5);
+  constexpr int c0765 = (int)((double)0.765366865f * F + 0.5), c1175 = (int)((double)1.175875602f * F + 0.5);
+  constexpr int c0298 = (int)((double)0.298631336f * F + 0.5), c2053 = (int)((double)2.053119869f * F + 0.5);
+  constexpr int c3072 = (int)((double)3.072711026f * F + 0.5), c1501 = (int)((double)1.501321110f * F + 0.5);
+  constexpr int c0899 = (int)((double)-0.899976223f * F + 0.5), c2562 = (int)((double)-2.562915447f * F + 0.5);
+  constexpr int c1961 = (int)((double)-1.961570560f * F + 0.5), c0390 = (int)((double)-0.390180644f * F + 0.5);
   const int s0 = s[0], s1 = s[stride], s2 = s[2 * stride], s3 = s[3 * stride], s4 = s[4 * stride], s5 = s[5 * stride],
             s6 = s[6 * stride], s7 = s[7 * stride];
   // even part
@@ -159,6 +162,11 @@ static void idct8x8(const int16_t* coef, uint8_t* out, int stride) {
   int col[64], in[64];
   for (int i = 0; i < 64; i++) in[i] = coef[i];
   for (int x = 0; x < 8; x++) {  // columns; keep two extra bits
+    if (!(in[x + 8] | in[x + 16] | in[x + 24] | in[x + 32] | in[x + 40] | in[x + 48] | in[x + 56])) {
+      const int dc = in[x] * 4;  // a column with only its DC term: (dc * 4096 + 512) >> 10 in every row
+      for (int k = 0; k < 8; k++) col[k * 8 + x] = dc;
+      continue;
+    }
     int e[4], o[4];
     llm_1d(in + x, 8, e, o);
     for (int k = 0; k < 4; k++) {
@@ -446,6 +454,10 @@ inline bool decode_jpeg(const uint8_t* d, size_t n, GrayImage& out) {
     const JComp& C = comp[c];
     return plane[c][(size_t)(y * C.v / vmax) * (C.bw * 8) + (size_t)(x * C.h / hmax)];
   };
+  if (!rgb && comp[0].h == hmax && comp[0].v == vmax) {  // the usual case: the plane is at image resolution
+    for (int y = 0; y < H; y++) memcpy(&out.pix[(size_t)y * W], &plane[0][(size_t)y * comp[0].bw * 8], (size_t)W);
+    return true;
+  }
   for (int y = 0; y < H; y++)
     for (int x = 0; x < W; x++)
       out.pix[(size_t)y * W + x] = rgb ? luma8(at(0, x, y), at(1, x, y), at(2, x, y)) : at(0, x, y);
