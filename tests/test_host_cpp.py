@@ -183,6 +183,37 @@ def test_programs_parse_reference_inputs(built, tmp_path):
     assert r.returncode == 1 and "cannot open" in r.stderr
 
 
+def test_keff2d_program_accepts_the_formats_the_reference_reads(built, tmp_path):
+    """InputName may be a progressive JPEG, a PNG or a BMP (stb_image reads them, Keff2D/keff2D.h:300): the drop-in
+    program thresholds the same bytes -- checked through the porosity it prints for a structure saved losslessly."""
+    from PIL import Image
+    from keff_cfd_b200 import structures as S
+    d = str(tmp_path)
+    img = S.to_gray(S.disc_image(7, n=96))[:80, :]
+    fluid = float((img < 150).mean())
+    for name in ("s.png", "s.pgm"):
+        Image.fromarray(img).save(os.path.join(d, name))
+        open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name=name, tmap=0, batch=0, nimg=1))
+        r = subprocess.run([os.path.join(built, "keff2D"), "--check-inputs"], cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, (name, r.stderr)
+        assert "96x80 porosity %.10f cells 7680" % fluid in r.stdout, (name, r.stdout)
+    # a palettised BMP decodes to 3 channels in the reference's decoder: single-image mode refuses it exactly as the
+    # reference does (Keff2D/keff2D.cpp:60-63)
+    Image.fromarray(img).save(os.path.join(d, "s.bmp"))
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name="s.bmp", tmap=0, batch=0, nimg=1))
+    r = subprocess.run([os.path.join(built, "keff2D"), "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "Current number of channels = 3" in r.stdout
+    Image.fromarray(img).save(os.path.join(d, "p.jpg"), quality=95, progressive=True)   # lossy: against the decoded bytes
+    a, c = _decode(built, os.path.join(d, "p.jpg"), d)
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name="p.jpg", tmap=0, batch=0, nimg=1))
+    r = subprocess.run([os.path.join(built, "keff2D"), "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0 and "96x80 porosity %.10f cells 7680" % float((a < 150).mean()) in r.stdout, r.stdout + r.stderr
+    open(os.path.join(d, "bad.gif"), "wb").write(b"GIF89a" + bytes(40))
+    open(os.path.join(d, "input.txt"), "w").write(INPUT_2D.format(amp=1, name="bad.gif", tmap=0, batch=0, nimg=1))
+    r = subprocess.run([os.path.join(built, "keff2D"), "--check-inputs"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "unrecognised image format" in r.stderr
+
+
 @pytest.mark.gpu
 def test_keff2d_program_end_to_end(built, tmp_path):
     d = str(tmp_path)
