@@ -58,6 +58,48 @@ def hierarchy(solid, ks=10.0, kf=1.0):
     return levels, np.linalg.inv(A)
 
 
+def dense_matrix(L):
+    """The dense-level matrix the kernel assembles in shared memory (5-point operator of the coarsest level)."""
+    n = L.d.size
+    A = np.zeros((n, n))
+    for i in range(n):
+        e = np.zeros(n); e[i] = 1
+        A[:, i] = L.apply(e.reshape(L.d.shape)).ravel()
+    return A
+
+
+def block_gauss_jordan(A, dtype=np.float32, bs=8):
+    """In-place inverse the way k_batch2d_mg forms it (batch2d_mg.cuh): the matrix padded to 64 x 64 with an identity,
+    one step per 8 x 8 pivot block, no pivoting (SPD M-matrix).  Step kb with P = (pivot block)^-1, C = the pivot
+    columns, R = the pivot rows:  pivot rows <- P R (pivot columns: P);  every other row i <- (row with its pivot
+    columns zeroed) - C_i (P R with its pivot columns replaced by P).  P itself by eight scalar Gauss-Jordan steps."""
+    na = A.shape[0]
+    M = np.zeros((64, 64), dtype)
+    M[:na, :na] = A
+    for i in range(na, 64):
+        M[i, i] = 1
+    for kb in range((na + bs - 1) // bs):
+        s = slice(bs * kb, bs * kb + bs)
+        P = M[s, s].copy()
+        for p in range(bs):
+            piv = dtype(1) / P[p, p]
+            row, col = P[p, :] * piv, P[:, p].copy()
+            row[p] = piv
+            keep = P.copy()
+            keep[:, p] = 0
+            P = (keep - np.outer(col, row)).astype(dtype)
+            P[p, :] = row
+        T = (P @ M[s, :]).astype(dtype)
+        T[:, s] = P
+        C = M[:, s].copy()
+        keep = M.copy()
+        keep[:, s] = 0
+        new = (keep - C @ T).astype(dtype)
+        new[s, :] = T
+        M = new
+    return M[:na, :na]
+
+
 def restrict(r):
     return r[0::2, 0::2] + r[0::2, 1::2] + r[1::2, 0::2] + r[1::2, 1::2]
 

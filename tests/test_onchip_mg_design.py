@@ -38,3 +38,17 @@ def test_two_sweeps_on_the_coarse_levels_pay():
     _, it22, _ = P.pcg(img)
     _, it11, _ = P.pcg(img, wc=(0.8,))                      # one sweep per side everywhere
     assert it22 < it11 <= 22
+
+
+def test_block_gauss_jordan_is_the_dense_level_inverse():
+    """The kernel inverts the coarsest-level matrix by block Gauss-Jordan with 8 x 8 pivot blocks in FP32, padded with
+    an identity: same inverse as LAPACK's to single precision, symmetric, for every dense-level shape it meets."""
+    for ny, nx in ((128, 128), (48, 80), (16, 16), (128, 16), (112, 128)):
+        img = S.disc_image(4)[:ny, :nx]
+        levels, _ = P.hierarchy(img)
+        A = P.dense_matrix(levels[-1])
+        inv = P.block_gauss_jordan(A)
+        ref = np.linalg.inv(A)
+        assert inv.shape == (ny // 16 * (nx // 16),) * 2
+        assert np.abs(inv - ref).max() <= 2e-6 * np.abs(ref).max()
+        assert np.abs(inv - inv.T).max() <= 2e-6 * np.abs(ref).max()
