@@ -94,16 +94,45 @@ inline void structure_from_image(const GrayImage& g, int ampX, int ampY, std::ve
 
 // 3D structure: text lines "x,y,z" of solid voxels (readImage3D, Keff3D/keff3D.h:237-280).
 inline bool structure_from_csv(const std::string& path, int W, int H, int D, std::vector<uint8_t>& solid, std::string& err) {
-  FILE* f = fopen(path.c_str(), "r");
+  FILE* f = fopen(path.c_str(), "rb");
   if (!f) { err = "cannot open " + path; return false; }
+  std::vector<char> buf;
+  {
+    char tmp[1 << 16];
+    size_t r;
+    while ((r = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + r);
+  }
+  fclose(f);
+  buf.push_back('\0');
   solid.assign((size_t)W * H * D, 0);
-  int x, y, z;
+  // the reference reads with fscanf(" %d,%d,%d") until it fails: same grammar (white space, optional sign, digits,
+  // commas), same stop at the first thing that is not a triple -- parsed in place (a 512^3 structure has 10^8 lines)
+  const char* p = buf.data();
+  auto skip_ws = [&]() { while (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t' || *p == '\f' || *p == '\v') p++; };
+  auto integer = [&](int& v) -> bool {
+    skip_ws();
+    bool neg = false;
+    if (*p == '-' || *p == '+') neg = *p++ == '-';
+    if (*p < '0' || *p > '9') return false;
+    long t = 0;
+    while (*p >= '0' && *p <= '9') {
+      if (t < (1L << 40)) t = t * 10 + (*p - '0');
+      p++;
+    }
+    v = (int)(neg ? -t : t);
+    return true;
+  };
   size_t bad = 0;
-  while (fscanf(f, " %d,%d,%d", &x, &y, &z) == 3) {
+  int x, y, z;
+  while (true) {
+    if (!integer(x) || *p != ',') break;
+    p++;
+    if (!integer(y) || *p != ',') break;
+    p++;
+    if (!integer(z)) break;
     if (x < 0 || y < 0 || z < 0 || x >= W || y >= H || z >= D) { bad++; continue; }
     solid[((size_t)z * H + y) * W + x] = 1;
   }
-  fclose(f);
   if (bad) { err = "coordinates outside Width/Height/Depth in " + path; return false; }
   return true;
 }
