@@ -175,8 +175,9 @@ int keffb200_flux_field(const uint8_t* solid, int nx, int ny, int nz, const keff
  * SolExpandSimple (Keff2D/keff2D.h:614-642), which replicates values without interpolating.  Host buffers. */
 int keffb200_interpolate(const double* T_src, int sx, int sy, int sz, double* T_dst, int nx, int ny, int nz,
                          double tl, double tr);
-/* Page-locked host memory for the buffers handed to the host-buffer entry points (optional: pageable memory works,
- * but its copies are staged by the driver and do not overlap with the solves). */
+/* Page-locked host memory for the buffers handed to the host-buffer entry points (optional: pageable memory works;
+ * keffb200_solve2d_batch streams a batch to the GPU in chunks underneath its solve from either kind, a volume's
+ * single copy is faster from page-locked memory). */
 void* keffb200_host_alloc(size_t bytes);
 void keffb200_host_free(void* p);
 
